@@ -1,0 +1,148 @@
+/*
+ * mas_b200.h -- C ABI of the B200-native VITS2 alignment hot path
+ * (neg_cent cost + monotonic alignment search).
+ *
+ * This is the drop-in boundary: what a maintainer of kgoba/torch-tts would bind
+ * instead of the Cython extension `vits2/monotonic_align/core.pyx`.  Plain
+ * pointers and sizes only; no torch types.  All data pointers are DEVICE
+ * pointers on the current CUDA device unless stated otherwise; every call is
+ * stream-ordered on `stream` (a cudaStream_t passed as void*), never
+ * synchronises the host, and is re-entrant across streams and devices.
+ *
+ * Citations are relative to the reference tree (kgoba/torch-tts).
+ *
+ * Tensors (all C-contiguous):
+ *   neg_cent [B, T, S] float32   cost plane, T = mel frames (reference t_t/t_y),
+ *                                S = text tokens (reference t_s/t_x), S contiguous
+ *   z_p      [B, D, T] float32   flow output, T contiguous      (models.py:1222)
+ *   m_p      [B, D, S] float32   prior mean,   S contiguous     (models.py:1220)
+ *   logs_p   [B, D, S] float32   prior log-std                  (models.py:1220)
+ *   t_ys     [B] int32           mel lengths  (reference t_t_max, __init__.py:16)
+ *   t_xs     [B] int32           text lengths (reference t_s_max, __init__.py:17)
+ *   path     [B, T, S]           {0,1}, dtype selected by `path_dtype`
+ *   dur      [B, S] int32        path.sum over T  (w of models.py:1256)
+ *   idx      [B, T] int32        compact path: text column of mel row y, -1 for y >= t_y
+ *   status   [B] int32           per-utterance MAS_UTT_* code (0 = aligned)
+ *
+ * Length contract: the reference is undefined behaviour unless
+ * 1 <= t_x <= t_y <= T and t_x <= S (core.pyx:30-33 reads value[-1,..] /
+ * writes path[y,-1] otherwise).  This library never emulates that: an
+ * utterance that violates the contract gets an all-zero path, zero durations,
+ * idx = -1 and status[b] = MAS_UTT_BAD_LENGTHS.
+ */
+#ifndef MAS_B200_H_
+#define MAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* return codes (host-detectable argument errors; 0 = launched) */
+enum {
+    MAS_OK = 0,
+    MAS_ERR_NULL_POINTER = 1,
+    MAS_ERR_BAD_SHAPE = 2,        /* B, T, S or D < 1 */
+    MAS_ERR_UNSUPPORTED_SHAPE = 3,/* S > MAS_MAX_TEXT, T > MAS_MAX_MEL, D not supported */
+    MAS_ERR_ALIGNMENT = 4,        /* a base pointer is not 16-byte aligned */
+    MAS_ERR_WORKSPACE = 5,        /* workspace NULL or smaller than the *_workspace_bytes() answer */
+    MAS_ERR_BAD_DTYPE = 6,
+    MAS_ERR_CUDA = 7              /* a CUDA runtime call failed; see mas_last_cuda_error() */
+};
+
+/* per-utterance device status */
+enum {
+    MAS_UTT_OK = 0,
+    MAS_UTT_BAD_LENGTHS = 1
+};
+
+/* dtype of the dense path written by the library (reference returns
+ * neg_cent.dtype: __init__.py:19) */
+enum {
+    MAS_PATH_F32 = 0,
+    MAS_PATH_F16 = 1,
+    MAS_PATH_BF16 = 2,
+    MAS_PATH_I32 = 3              /* the int32 plane core.pyx itself fills */
+};
+
+#define MAS_MAX_TEXT 1024         /* S  */
+#define MAS_MAX_MEL 65535         /* T  */
+
+int mas_b200_abi_version(void);
+const char *mas_status_string(int code);
+/* text of the last CUDA error seen by this thread inside the library */
+const char *mas_last_cuda_error(void);
+
+/*
+ * Lengths from the reference's dense mask (replaces __init__.py:16-17:
+ * t_y = mask.sum(1)[:,0], t_x = mask.sum(2)[:,0]).  Reads only column 0 and
+ * row 0 of each mask plane (T + S elements, not T*S).
+ */
+int mas_lengths_from_mask_f32(const float *mask, int32_t *t_ys, int32_t *t_xs,
+                              int B, int T, int S, void *stream);
+
+/*
+ * Replaces maximum_path_c (core.pyx:38-42) plus the zero-init and dtype cast
+ * of the Python wrapper (__init__.py:14,19).
+ *   - neg_cent is read-only (the reference's in-place DP works on a private copy,
+ *     __init__.py:13).
+ *   - path_out is fully written (zeros included); it need not be pre-zeroed.
+ *   - dur_out, idx_out, status_out may be NULL.
+ *   - workspace: mas_maximum_path_workspace_bytes(B,T,S) bytes, 256-byte aligned.
+ */
+size_t mas_maximum_path_workspace_bytes(int B, int T, int S);
+int mas_maximum_path_f32(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs,
+                         void *path_out, int path_dtype,
+                         int32_t *dur_out, int32_t *idx_out, int32_t *status_out,
+                         void *workspace, size_t workspace_bytes,
+                         int B, int T, int S, void *stream);
+
+/*
+ * The cost block of SynthesizerTrn.forward (models.py:1226-1239):
+ *   neg_cent[b,t,s] = sum_d [ -0.5*log(2*pi) - logs_p - 0.5*(z_p - m_p)^2 * exp(-2*logs_p) ]
+ * evaluated as the reference does (two contractions over D plus two column
+ * biases).  If stats_out != NULL it receives {sum, sum of squares} of all
+ * B*T*S cells as two float64 (device), for the noise std of models.py:1243.
+ */
+size_t mas_neg_cent_workspace_bytes(int B, int D, int T, int S);
+int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p,
+                     float *neg_cent_out, double *stats_out,
+                     void *workspace, size_t workspace_bytes,
+                     int B, int D, int T, int S, void *stream);
+
+/*
+ * The SynthesizerTrn alignment call as one unit (models.py:1224-1256):
+ * cost -> optional VITS2 noise -> MAS -> path (+ durations, compact idx).
+ *   - noise: NULL (mas_noise_scale is None) or the torch.randn_like draw
+ *     [B,T,S] float32 supplied by the caller (models.py:1244); the library
+ *     computes std over all B*T*S cells (unbiased, padding included, :1243)
+ *     and adds (std * noise) * noise_scale (:1242-1247).
+ *   - neg_cent_out: optional [B,T,S] float32 copy of the cost actually aligned.
+ */
+size_t mas_fused_align_workspace_bytes(int B, int D, int T, int S, int with_noise);
+int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
+                        const int32_t *t_ys, const int32_t *t_xs,
+                        const float *noise, float noise_scale,
+                        void *path_out, int path_dtype,
+                        int32_t *dur_out, int32_t *idx_out, int32_t *status_out,
+                        float *neg_cent_out,
+                        void *workspace, size_t workspace_bytes,
+                        int B, int D, int T, int S, void *stream);
+
+/*
+ * Compact <-> dense helpers for the multi-GPU path:
+ * ranks all-gather idx [B,T] int32 and re-expand locally.
+ */
+int mas_expand_path(const int32_t *idx, void *path_out, int path_dtype,
+                    int B, int T, int S, void *stream);
+
+/* number of kernels this library launched on the calling thread since the
+ * last call (bench.py's gpu_launches); resets the counter. */
+long mas_take_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAS_B200_H_ */

@@ -1,0 +1,98 @@
+"""The SynthesizerTrn alignment call as one unit (reference vits2/models.py:1224-1256):
+cost -> optional VITS2 noise-scaled MAS -> path and durations.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _lengths(x_mask, y_mask):
+    # what mask.sum(1)[:,0] / mask.sum(2)[:,0] give for attn_mask = x_mask[:,:,None] * y_mask[...,None]
+    # (models.py:1249, __init__.py:16-17)
+    xm = x_mask.reshape(x_mask.shape[0], -1).float()
+    ym = y_mask.reshape(y_mask.shape[0], -1).float()
+    t_ys = (ym.sum(1) * xm[:, 0]).to(torch.int32)
+    t_xs = (xm.sum(1) * ym[:, 0]).to(torch.int32)
+    return t_ys, t_xs
+
+
+def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torch.Tensor:
+    """models.py:1226-1239 -> [B, T, S] float32."""
+    for n, t in (("z_p", z_p), ("m_p", m_p), ("logs_p", logs_p)):
+        _lib.require_cuda(t, n)
+    B, D, T = z_p.shape
+    S = m_p.shape[2]
+    device = z_p.device
+    z, m, l = (t.detach().float().contiguous() for t in (z_p, m_p, logs_p))
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        out = torch.empty((B, T, S), dtype=torch.float32, device=device)
+        nbytes = L.mas_neg_cent_workspace_bytes(B, D, T, S)
+        if nbytes == 0:
+            raise _lib.MasError(f"unsupported shape B={B} D={D} T={T} S={S}")
+        ws = _lib.workspace(device, nbytes)
+        rc = L.mas_neg_cent_f32(_lib.ptr(z), _lib.ptr(m), _lib.ptr(l), _lib.ptr(out), None, _lib.ptr(ws),
+                                ws.numel(), B, D, T, S, _lib.stream_ptr(device))
+    _lib.check(rc, "mas_neg_cent_f32")
+    return out
+
+
+def align(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=None, *,
+          x_lengths=None, y_lengths=None, return_compact: bool = False, return_neg_cent: bool = False):
+    """Replacement for models.py:1224-1256.
+
+    z_p [B,D,T], m_p/logs_p [B,D,S], x_mask [B,1,S], y_mask [B,1,T].
+    mas_noise_scale: None, or the scalar of cli.py:268-271 (0 still takes the
+    noise branch, as in the reference).  noise: optional [B,T,S] draw standing
+    in for torch.randn_like(neg_cent) (models.py:1244); drawn here when absent.
+    Returns (attn [B,1,T,S] in z_p.dtype, w [B,1,S]) and, on request, the
+    compact (idx, durations, status) and the aligned neg_cent.
+    """
+    for n, t in (("z_p", z_p), ("m_p", m_p), ("logs_p", logs_p)):
+        _lib.require_cuda(t, n)
+    B, D, T = z_p.shape
+    S = m_p.shape[2]
+    device, dtype = z_p.device, z_p.dtype
+    with torch.no_grad():
+        z, m, l = (t.detach().float().contiguous() for t in (z_p, m_p, logs_p))
+        if x_lengths is not None and y_lengths is not None:
+            t_xs = x_lengths.to(device=device, dtype=torch.int32)
+            t_ys = y_lengths.to(device=device, dtype=torch.int32)
+        else:
+            t_ys, t_xs = _lengths(x_mask.to(device), y_mask.to(device))
+        nz = None
+        scale = 0.0
+        if mas_noise_scale is not None:
+            scale = float(mas_noise_scale)
+            nz = noise if noise is not None else torch.randn((B, T, S), dtype=torch.float32, device=device)
+            nz = nz.to(device=device, dtype=torch.float32).contiguous()
+        kdtype = dtype if dtype in _lib.PATH_DTYPES else torch.float32
+        L = _lib.lib()
+        with torch.cuda.device(device):
+            path = torch.empty((B, T, S), dtype=kdtype, device=device)
+            dur = torch.empty((B, S), dtype=torch.int32, device=device)
+            idx = torch.empty((B, T), dtype=torch.int32, device=device)
+            status = torch.empty((B,), dtype=torch.int32, device=device)
+            nc_out = torch.empty((B, T, S), dtype=torch.float32, device=device) if return_neg_cent else None
+            nbytes = L.mas_fused_align_workspace_bytes(B, D, T, S, int(nz is not None))
+            if nbytes == 0:
+                raise _lib.MasError(f"unsupported shape B={B} D={D} T={T} S={S}")
+            ws = _lib.workspace(device, nbytes)
+            rc = L.mas_fused_align_f32(_lib.ptr(z), _lib.ptr(m), _lib.ptr(l), _lib.ptr(t_ys.contiguous()),
+                                       _lib.ptr(t_xs.contiguous()), _lib.ptr(nz), scale, _lib.ptr(path),
+                                       _lib.PATH_DTYPES[kdtype], _lib.ptr(dur), _lib.ptr(idx), _lib.ptr(status),
+                                       _lib.ptr(nc_out), _lib.ptr(ws), ws.numel(), B, D, T, S,
+                                       _lib.stream_ptr(device))
+        _lib.check(rc, "mas_fused_align_f32")
+        if kdtype != dtype:
+            path = path.to(dtype)
+        attn = path.unsqueeze(1)                       # models.py:1252
+        w = dur.to(dtype).unsqueeze(1)                 # models.py:1256  attn.sum(2)
+    out = (attn, w)
+    if return_compact:
+        out = out + ((idx, dur, status),)
+    if return_neg_cent:
+        out = out + (nc_out,)
+    return out

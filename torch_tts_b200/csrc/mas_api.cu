@@ -1,0 +1,179 @@
+// mas_api.cu -- the extern "C" surface declared in include/mas_b200.h.
+// Argument validation on the host, then stream-ordered kernel launches; no
+// host synchronisation, no CPU fallback.
+#include <stdio.h>
+#include <string.h>
+
+#include "mas_common.cuh"
+
+namespace mas {
+
+static thread_local long g_launches = 0;
+static thread_local char g_cuda_err[256] = "";
+
+void note_launch(int n) { g_launches += n; }
+
+int note_cuda_error(cudaError_t e, const char *what)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return MAS_ERR_CUDA;
+}
+
+// mas_dp.cu
+size_t dp_workspace_bytes(int B, int T, int S);
+int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
+              int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace, size_t workspace_bytes, int B,
+              int T, int S, cudaStream_t stream);
+int lengths_launch(const float *mask, int32_t *t_ys, int32_t *t_xs, int B, int T, int S, cudaStream_t stream);
+int expand_launch(const int32_t *idx, void *path_out, int path_dtype, int B, int T, int S, cudaStream_t stream);
+// mas_cost.cu
+size_t cost_workspace_bytes(int B, int D, int T, int S);
+int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
+                void *workspace, size_t workspace_bytes, int B, int D, int T, int S, cudaStream_t stream);
+int add_noise_launch(const float *nc, const float *noise, const double *stats, float scale, float *out, size_t n,
+                     cudaStream_t stream);
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int check_shape(int B, int T, int S)
+{
+    if (B < 1 || T < 1 || S < 1) return MAS_ERR_BAD_SHAPE;
+    if (S > MAS_MAX_TEXT || T > MAS_MAX_MEL) return MAS_ERR_UNSUPPORTED_SHAPE;
+    return MAS_OK;
+}
+
+static int check_dtype(int path_dtype)
+{
+    return (path_dtype >= MAS_PATH_F32 && path_dtype <= MAS_PATH_I32) ? MAS_OK : MAS_ERR_BAD_DTYPE;
+}
+
+}  // namespace mas
+
+using namespace mas;
+
+extern "C" {
+
+int mas_b200_abi_version(void) { return 1; }
+
+const char *mas_status_string(int code)
+{
+    switch (code) {
+        case MAS_OK: return "ok";
+        case MAS_ERR_NULL_POINTER: return "null pointer argument";
+        case MAS_ERR_BAD_SHAPE: return "B, T, S and D must be >= 1";
+        case MAS_ERR_UNSUPPORTED_SHAPE: return "shape outside the supported range (S <= 1024, T <= 65535)";
+        case MAS_ERR_ALIGNMENT: return "base pointer must be 16-byte aligned";
+        case MAS_ERR_WORKSPACE: return "workspace missing or too small";
+        case MAS_ERR_BAD_DTYPE: return "unknown path dtype";
+        case MAS_ERR_CUDA: return "CUDA runtime error (see mas_last_cuda_error)";
+    }
+    return "unknown status";
+}
+
+const char *mas_last_cuda_error(void) { return g_cuda_err; }
+
+long mas_take_launch_count(void)
+{
+    long n = g_launches;
+    g_launches = 0;
+    return n;
+}
+
+int mas_lengths_from_mask_f32(const float *mask, int32_t *t_ys, int32_t *t_xs, int B, int T, int S, void *stream)
+{
+    if (!mask || !t_ys || !t_xs) return MAS_ERR_NULL_POINTER;
+    if (B < 1 || T < 1 || S < 1) return MAS_ERR_BAD_SHAPE;
+    return lengths_launch(mask, t_ys, t_xs, B, T, S, static_cast<cudaStream_t>(stream));
+}
+
+size_t mas_maximum_path_workspace_bytes(int B, int T, int S)
+{
+    if (check_shape(B, T, S) != MAS_OK) return 0;
+    return dp_workspace_bytes(B, T, S);
+}
+
+int mas_maximum_path_f32(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
+                         int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
+                         size_t workspace_bytes, int B, int T, int S, void *stream)
+{
+    if (!neg_cent || !t_ys || !t_xs || !path_out) return MAS_ERR_NULL_POINTER;
+    int rc = check_shape(B, T, S);
+    if (rc) return rc;
+    rc = check_dtype(path_dtype);
+    if (rc) return rc;
+    if (!aligned16(neg_cent) || !aligned16(workspace)) return MAS_ERR_ALIGNMENT;
+    return dp_launch(neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, workspace,
+                     workspace_bytes, B, T, S, static_cast<cudaStream_t>(stream));
+}
+
+size_t mas_neg_cent_workspace_bytes(int B, int D, int T, int S)
+{
+    if (check_shape(B, T, S) != MAS_OK || D < 1) return 0;
+    return cost_workspace_bytes(B, D, T, S);
+}
+
+int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
+                     void *workspace, size_t workspace_bytes, int B, int D, int T, int S, void *stream)
+{
+    if (!z_p || !m_p || !logs_p || !neg_cent_out) return MAS_ERR_NULL_POINTER;
+    int rc = check_shape(B, T, S);
+    if (rc) return rc;
+    if (D < 1) return MAS_ERR_BAD_SHAPE;
+    if (!aligned16(z_p) || !aligned16(m_p) || !aligned16(logs_p) || !aligned16(neg_cent_out) || !aligned16(workspace))
+        return MAS_ERR_ALIGNMENT;
+    return cost_launch(z_p, m_p, logs_p, neg_cent_out, stats_out, workspace, workspace_bytes, B, D, T, S,
+                       static_cast<cudaStream_t>(stream));
+}
+
+// fused workspace layout: [cost ws][stats 256 B][neg_cent plane][dp ws]
+size_t mas_fused_align_workspace_bytes(int B, int D, int T, int S, int with_noise)
+{
+    (void)with_noise;
+    if (check_shape(B, T, S) != MAS_OK || D < 1) return 0;
+    return align_up(cost_workspace_bytes(B, D, T, S), 256) + 256 + align_up((size_t)B * T * S * 4, 256) +
+           align_up(dp_workspace_bytes(B, T, S), 256);
+}
+
+int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p, const int32_t *t_ys,
+                        const int32_t *t_xs, const float *noise, float noise_scale, void *path_out, int path_dtype,
+                        int32_t *dur_out, int32_t *idx_out, int32_t *status_out, float *neg_cent_out, void *workspace,
+                        size_t workspace_bytes, int B, int D, int T, int S, void *stream)
+{
+    if (!z_p || !m_p || !logs_p || !t_ys || !t_xs || !path_out) return MAS_ERR_NULL_POINTER;
+    int rc = check_shape(B, T, S);
+    if (rc) return rc;
+    if (D < 1) return MAS_ERR_BAD_SHAPE;
+    rc = check_dtype(path_dtype);
+    if (rc) return rc;
+    if (!aligned16(z_p) || !aligned16(m_p) || !aligned16(logs_p) || !aligned16(workspace) ||
+        (noise && !aligned16(noise)) || (neg_cent_out && !aligned16(neg_cent_out)))
+        return MAS_ERR_ALIGNMENT;
+    if (!workspace || workspace_bytes < mas_fused_align_workspace_bytes(B, D, T, S, noise != nullptr))
+        return MAS_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    const size_t cost_ws = align_up(cost_workspace_bytes(B, D, T, S), 256);
+    double *stats = reinterpret_cast<double *>(ws + cost_ws);
+    float *nc = neg_cent_out ? neg_cent_out : reinterpret_cast<float *>(ws + cost_ws + 256);
+    unsigned char *dp_ws = ws + cost_ws + 256 + align_up((size_t)B * T * S * 4, 256);
+    const size_t dp_ws_bytes = align_up(dp_workspace_bytes(B, T, S), 256);
+    rc = cost_launch(z_p, m_p, logs_p, nc, noise ? stats : nullptr, ws, cost_ws, B, D, T, S, st);
+    if (rc) return rc;
+    if (noise) {
+        rc = add_noise_launch(nc, noise, stats, noise_scale, nc, (size_t)B * T * S, st);
+        if (rc) return rc;
+    }
+    return dp_launch(nc, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T, S,
+                     st);
+}
+
+int mas_expand_path(const int32_t *idx, void *path_out, int path_dtype, int B, int T, int S, void *stream)
+{
+    if (!idx || !path_out) return MAS_ERR_NULL_POINTER;
+    if (B < 1 || T < 1 || S < 1) return MAS_ERR_BAD_SHAPE;
+    int rc = check_dtype(path_dtype);
+    if (rc) return rc;
+    return expand_launch(idx, path_out, path_dtype, B, T, S, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

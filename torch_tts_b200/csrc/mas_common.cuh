@@ -1,0 +1,113 @@
+// mas_common.cuh -- shared device helpers (sm_100a only) for the MAS hot path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mas_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "mas_b200 kernels are written for sm_100a only"
+#endif
+
+namespace mas {
+
+constexpr float kNeg = -1e9f;  // core.pyx:7 max_neg_val (exactly representable)
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- host-side bookkeeping (defined in mas_api.cu) -------------------------
+void note_launch(int n = 1);
+int note_cuda_error(cudaError_t e, const char *what);
+
+#define MAS_CUDA_TRY(expr)                                        \
+    do {                                                          \
+        cudaError_t _e = (expr);                                  \
+        if (_e != cudaSuccess) return ::mas::note_cuda_error(_e, #expr); \
+    } while (0)
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void st_global_v4_zero(void *p)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(p), "r"(0u) : "memory");
+}
+
+__host__ __device__ __forceinline__ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ __forceinline__ int path_elem_size(int path_dtype)
+{
+    return (path_dtype == MAS_PATH_F16 || path_dtype == MAS_PATH_BF16) ? 2 : 4;
+}
+
+// bit pattern of "1" in the path dtype
+__host__ __device__ __forceinline__ uint32_t path_one_bits(int path_dtype)
+{
+    switch (path_dtype) {
+        case MAS_PATH_F32: return 0x3f800000u;
+        case MAS_PATH_F16: return 0x3c00u;
+        case MAS_PATH_BF16: return 0x3f80u;
+        default: return 1u;
+    }
+}
+
+}  // namespace mas

@@ -1,0 +1,578 @@
+// mas_dp.cu -- monotonic alignment search (forward DP + backtrack) for sm_100a.
+//
+// Replaces maximum_path_each / maximum_path_c of the reference
+// (vits2/monotonic_align/core.pyx:7-42) and the zero-init / dtype cast of its
+// Python wrapper (vits2/monotonic_align/__init__.py:14,19).  Bit-exact: per
+// cell one fp32 compare-select and one fp32 add, in the reference's operand
+// order; no FMA, no reassociation.
+//
+// Mapping (one CTA per utterance, 4 DP warps + 1 producer warp):
+//   * text columns are blocked over the 128 DP threads, C = ceil(S/128)
+//     consecutive columns per thread; the running DP row lives in registers.
+//   * the left neighbour crosses lanes with one __shfl_up per row and crosses
+//     warps through a small shared-memory ring; warp w runs one chunk of R mel
+//     rows behind warp w-1 (wavefront), one __syncthreads per chunk step.
+//   * the producer warp streams the cost plane through an 8-stage ring of
+//     shared-memory tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier)
+//     and zero-fills the dense path output while the DP runs.
+//   * 1 bit per cell (ballot of "took the diagonal") is kept on chip so the
+//     backtrack never re-reads the cost; every 32 rows the column each cell
+//     backtracks to ("hop") is checkpointed, so the backtrack is T/32 dependent
+//     hops followed by T/32 independent 32-row walks, one per thread.
+//   * long utterances whose bits/hops exceed shared memory spill them to the
+//     caller's workspace (L2-resident).
+#include "mas_common.cuh"
+
+namespace mas {
+
+constexpr int kDpWarps = 4;
+constexpr int kDpThreads = kDpWarps * 32;
+constexpr int kThreads = kDpThreads + 32;  // + producer warp
+constexpr int kStages = 8;
+constexpr int kCheck = 32;  // checkpoint interval (rows)
+constexpr int kSmemBudget = 227 * 1024;
+
+struct DpParams {
+    const float *neg_cent;
+    const int32_t *t_ys;
+    const int32_t *t_xs;
+    const int32_t *order;  // nullable: CTA -> utterance (longest first)
+    unsigned char *path;
+    int32_t *dur;
+    int32_t *idx;
+    int32_t *status;
+    uint32_t *bits_ws;      // global spill (per CTA region), used when !bits_in_smem
+    unsigned char *hop_ws;  // global spill (per CTA region), used when !hop_in_smem
+    int B, T, S;
+    int R;  // mel rows per chunk: 4, 8, 16 or 32
+    int path_dtype;
+    int bits_in_smem, hop_in_smem;
+    uint32_t off_bits, off_hop, off_stage, stage_bytes, off_bnd_v, off_bnd_o, off_idx, off_end, off_entry, off_bar;
+    unsigned long long bits_words_per_cta, hop_bytes_per_cta;
+};
+
+struct DpPlan {
+    DpParams p;
+    int C;
+    size_t smem_bytes;
+    size_t ws_bits_bytes, ws_hop_bytes;
+};
+
+// ---------------------------------------------------------------------------
+// host: shared-memory plan
+// ---------------------------------------------------------------------------
+static bool plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, bool hop_smem)
+{
+    const int S_pad = kDpThreads * C;
+    const int WPR = kDpWarps * C;
+    const int hop_rows = T / kCheck + 2;
+    size_t off = 0;
+    DpParams &p = pl.p;
+    p.R = R;
+    p.off_bar = (uint32_t)off;
+    off += 128;
+    p.off_bits = (uint32_t)off;
+    if (bits_smem) off += align_up((size_t)T * WPR * 4, 16);
+    p.off_hop = (uint32_t)off;
+    if (hop_smem) off += align_up((size_t)hop_rows * S_pad, 16);
+    p.stage_bytes = (uint32_t)align_up((size_t)R * S * 4 + 16 + (size_t)(S_pad - S) * 4 + 16, 128);
+    off = align_up(off, 128);
+    p.off_stage = (uint32_t)off;
+    off += (size_t)kStages * p.stage_bytes;
+    p.off_bnd_v = (uint32_t)off;
+    off += (size_t)(kDpWarps - 1) * 4 * R * 4;
+    p.off_bnd_o = (uint32_t)off;
+    off += (size_t)(kDpWarps - 1) * 4 * R * 4;
+    p.off_idx = (uint32_t)off;
+    off += align_up((size_t)T * 2, 16);
+    p.off_end = (uint32_t)off;
+    off += (size_t)S_pad * 4;
+    p.off_entry = (uint32_t)off;
+    off += align_up((size_t)hop_rows * 2, 16);
+    p.bits_in_smem = bits_smem;
+    p.hop_in_smem = hop_smem;
+    p.bits_words_per_cta = (unsigned long long)T * WPR;
+    p.hop_bytes_per_cta = (unsigned long long)align_up((size_t)hop_rows * S_pad, 16);
+    pl.smem_bytes = off;
+    pl.C = C;
+    return off <= (size_t)kSmemBudget;
+}
+
+// rows_hint > 0 forces the chunk height (tuning knob, MAS_DP_ROWS).
+static bool make_plan(DpPlan &pl, int B, int T, int S, int rows_hint)
+{
+    const int C = (S + kDpThreads - 1) / kDpThreads;
+    if (C < 1 || C > 8) return false;
+    const int rs_all[4] = {16, 8, 4, 32};
+    bool ok = false;
+    for (int mode = 0; mode < 3 && !ok; ++mode) {
+        const bool bits_smem = (mode == 0), hop_smem = (mode <= 1);
+        for (int i = 0; i < 3 && !ok; ++i) {
+            int R = rows_hint > 0 ? rows_hint : rs_all[i];
+            ok = plan_try(pl, T, S, C, R, bits_smem, hop_smem);
+            if (rows_hint > 0) break;
+        }
+    }
+    if (!ok) return false;
+    pl.ws_bits_bytes = pl.p.bits_in_smem ? 0 : (size_t)B * pl.p.bits_words_per_cta * 4;
+    pl.ws_hop_bytes = pl.p.hop_in_smem ? 0 : (size_t)B * pl.p.hop_bytes_per_cta;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void zero_bytes_warp(unsigned char *ptr, size_t bytes, int lane)
+{
+    // generic zero fill by one warp: 2-byte head/tail, 16-byte body
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(ptr) & 15)) & 15;
+    if (head > bytes) head = bytes;
+    for (size_t i = lane * 2; i < head; i += 64) *reinterpret_cast<uint16_t *>(ptr + i) = 0;
+    size_t body = (bytes - head) & ~(size_t)15;
+    for (size_t i = (size_t)lane * 16; i < body; i += 512) st_global_v4_zero(ptr + head + i);
+    for (size_t i = head + body + lane * 2; i < bytes; i += 64) *reinterpret_cast<uint16_t *>(ptr + i) = 0;
+}
+
+__device__ __forceinline__ void store_one(unsigned char *path_b, size_t cell, int path_dtype)
+{
+    if (path_dtype == MAS_PATH_F32)
+        reinterpret_cast<float *>(path_b)[cell] = 1.0f;
+    else if (path_dtype == MAS_PATH_I32)
+        reinterpret_cast<int32_t *>(path_b)[cell] = 1;
+    else
+        reinterpret_cast<uint16_t *>(path_b)[cell] = (uint16_t)path_one_bits(path_dtype);
+}
+
+// One mel row of the forward DP for this thread's C columns.
+//   v/org: running DP row and checkpoint origin per column (registers)
+//   cost:  neg_cent[y, x0..x0+C)
+//   left_v/left_o: value/origin of column x0-1 (used by lane 0 only)
+// Returns in `words` the ballot of the backtrack decision per column slot.
+template <int C, bool kEdge>
+__device__ __forceinline__ void dp_row(float (&v)[C], int (&org)[C], const float (&cost)[C], float left_v,
+                                       int left_o, int y, int x0, int lane, bool col0, uint32_t (&words)[C])
+{
+    float up_v = __shfl_up_sync(kFullMask, v[C - 1], 1);
+    int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
+    if (lane == 0) {
+        up_v = left_v;
+        up_o = left_o;
+    }
+#pragma unroll
+    for (int k = C - 1; k >= 0; --k) {
+        const float v_prev = (k == 0) ? up_v : v[k - 1];  // value[y-1, x-1]  (core.pyx:21-27)
+        const int o_prev = (k == 0) ? up_o : org[k - 1];
+        const float v_cur = v[k];                          // value[y-1, x]    (core.pyx:17-20)
+        // Cython's max(v_prev, v_cur): (v_cur > v_prev) ? v_cur : v_prev
+        const float m = (v_cur > v_prev) ? v_cur : v_prev;
+        // backtrack rule core.pyx:32: index != 0 and (index == y or value[y-1,x] < value[y-1,x-1])
+        bool diag = v_cur < v_prev;
+        if (kEdge) diag = diag || (x0 + k == y);
+        if (k == 0) diag = diag && !col0;
+        float nv = cost[k] + m;  // core.pyx:28
+        int no = diag ? o_prev : org[k];
+        if (kEdge) {
+            const bool in_band = (x0 + k <= y);  // upper band edge, core.pyx:16
+            nv = in_band ? nv : v_cur;
+            no = in_band ? no : org[k];
+        }
+        v[k] = nv;
+        org[k] = no;
+        words[k] = __ballot_sync(kFullMask, diag);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
+    const int T = p.T, S = p.S, R = p.R;
+    const int t_y = p.t_ys[b], t_x = p.t_xs[b];
+    constexpr int S_pad = kDpThreads * C;
+    constexpr int WPR = kDpWarps * C;
+    const int esize = path_elem_size(p.path_dtype);
+    const size_t plane = (size_t)T * S;
+    unsigned char *path_b = p.path + (size_t)b * plane * esize;
+
+    // ---- length contract (anything else is UB in the reference) ----
+    if (!(t_x >= 1 && t_x <= t_y && t_y <= T && t_x <= S)) {
+        {
+            const size_t total = plane * esize;
+            const size_t seg = align_up((total + kThreads / 32 - 1) / (kThreads / 32), 512);
+            size_t lo = (size_t)warp * seg, hi = lo + seg;
+            if (lo > total) lo = total;
+            if (hi > total) hi = total;
+            if (hi > lo) zero_bytes_warp(path_b + lo, hi - lo, lane);
+        }
+        if (p.dur)
+            for (int x = tid; x < S; x += kThreads) p.dur[(size_t)b * S + x] = 0;
+        if (p.idx)
+            for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = -1;
+        if (p.status && tid == 0) p.status[b] = MAS_UTT_BAD_LENGTHS;
+        return;
+    }
+
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint32_t *bits = p.bits_in_smem ? reinterpret_cast<uint32_t *>(smem + p.off_bits)
+                                    : p.bits_ws + (size_t)blockIdx.x * p.bits_words_per_cta;
+    unsigned char *hop = p.hop_in_smem ? (smem + p.off_hop) : p.hop_ws + (size_t)blockIdx.x * p.hop_bytes_per_cta;
+    float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);
+    int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
+    uint16_t *idx_s = reinterpret_cast<uint16_t *>(smem + p.off_idx);
+    int *end_s = reinterpret_cast<int *>(smem + p.off_end);
+    uint16_t *entry_s = reinterpret_cast<uint16_t *>(smem + p.off_entry);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int n_chunks = (t_y + R - 1) / R;
+    const int n_steps = n_chunks + kDpWarps - 1;
+    const int ring_mask = 4 * R - 1;
+    const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
+    const size_t total_bytes = (size_t)p.B * plane * 4;
+
+    if (warp == kDpWarps) {
+        // =================== producer warp ===================
+        auto issue_tile = [&](int c) {
+            const int row0 = c * R;
+            const int rows = min(R, t_y - row0);
+            const size_t start = (utt_elem0 + (size_t)row0 * S) * 4;
+            const uint32_t mis = (uint32_t)(start & 15);
+            const size_t src0 = start - mis;
+            const uint32_t want = mis + (uint32_t)rows * S * 4;
+            uint32_t bulk = (want + 15u) & ~15u;
+            unsigned char *dst = smem + p.off_stage + (size_t)(c % kStages) * p.stage_bytes;
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(p.neg_cent) + src0;
+            if (src0 + bulk > total_bytes) {
+                // the 16-byte round-up would run past the tensor: finish the tail by hand
+                bulk = want & ~15u;
+                for (uint32_t o = bulk; o < want; o += 4)
+                    *reinterpret_cast<float *>(dst + o) = *reinterpret_cast<const float *>(src + o);
+            }
+            mbar_arrive_expect_tx(&full[c % kStages], bulk);
+            if (bulk) bulk_g2s(dst, src, bulk, &full[c % kStages]);
+        };
+        if (lane == 0) {
+            const int pre = min(kStages, n_chunks);
+            for (int c = 0; c < pre; ++c) issue_tile(c);
+        }
+        // zero-fill of the dense path, spread over the chunk steps
+        const size_t pbytes = plane * esize;
+        const size_t quota = align_up((pbytes + n_steps - 1) / n_steps, 512);
+        for (int step = 0; step < n_steps; ++step) {
+            size_t lo = (size_t)step * quota, hi = lo + quota;
+            if (lo > pbytes) lo = pbytes;
+            if (hi > pbytes || step == n_steps - 1) hi = pbytes;
+            if (hi > lo) zero_bytes_warp(path_b + lo, hi - lo, lane);
+            __syncthreads();
+            const int freed = step - (kDpWarps - 1);
+            if (lane == 0 && freed >= 0 && freed + kStages < n_chunks) issue_tile(freed + kStages);
+        }
+    } else {
+        // =================== DP warps ===================
+        const int w = warp;
+        const int x0 = (w * 32 + lane) * C;
+        const bool col0 = (x0 == 0);
+        float v[C];
+        int org[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            v[k] = kNeg;
+            org[k] = x0 + k;
+        }
+        for (int step = 0; step < n_steps; ++step) {
+            const int c = step - w;
+            if (c >= 0 && c < n_chunks) {
+                const int row0 = c * R;
+                const int rows = min(R, t_y - row0);
+                const uint32_t mis = (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
+                const float *tile = reinterpret_cast<const float *>(smem + p.off_stage +
+                                                                    (size_t)(c % kStages) * p.stage_bytes + mis);
+                mbar_wait(&full[c % kStages], (uint32_t)(c / kStages) & 1u);
+                const bool edge = row0 < S_pad;
+                // checkpoint rows are multiples of 32 and R divides 32 (or is 32): only a chunk's row 0 can be one
+                for (int r = 0; r < rows; r += 4) {
+                    float cost[4][C];
+                    float lv[4];
+                    int lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (r + i < rows) {
+#pragma unroll
+                            for (int k = 0; k < C; ++k) cost[i][k] = tile[(size_t)(r + i) * S + x0 + k];
+                        }
+                        const int y = row0 + r + i;
+                        if (w == 0) {
+                            lv[i] = (y == 0) ? 0.0f : kNeg;  // core.pyx:21-25
+                            lo[i] = 0;
+                        } else {
+                            lv[i] = bnd_v[(w - 1) * 4 * R + (y & ring_mask)];
+                            lo[i] = bnd_o[(w - 1) * 4 * R + (y & ring_mask)];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (r + i < rows) {
+                            const int y = row0 + r + i;
+                            uint32_t words[C];
+                            if (edge)
+                                dp_row<C, true>(v, org, cost[i], lv[i], lo[i], y, x0, lane, col0, words);
+                            else
+                                dp_row<C, false>(v, org, cost[i], lv[i], lo[i], y, x0, lane, col0, words);
+                            if (lane == 0) {
+#pragma unroll
+                                for (int k = 0; k < C; ++k) bits[(size_t)y * WPR + w * C + k] = words[k];
+                            }
+                            if (((y & (kCheck - 1)) == 0) && y > 0) {
+                                unsigned char *hrow = hop + (size_t)(y / kCheck) * S_pad;
+#pragma unroll
+                                for (int k = 0; k < C; ++k) {
+                                    hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                                    org[k] = x0 + k;
+                                }
+                            }
+                            if (w < kDpWarps - 1 && lane == 31) {
+                                bnd_v[w * 4 * R + ((y + 1) & ring_mask)] = v[C - 1];
+                                bnd_o[w * 4 * R + ((y + 1) & ring_mask)] = org[C - 1];
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // origin of the last row relative to its checkpoint -> hop row 0
+#pragma unroll
+        for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
+    }
+    if (!p.bits_in_smem || !p.hop_in_smem) __threadfence_block();
+    __syncthreads();
+
+    // =================== backtrack ===================
+    const int y_last = t_y - 1;
+    const int J = y_last / kCheck;
+    if (tid == 0) {
+        // level 1: one dependent load per 32 rows
+        int c = t_x - 1;
+        c -= hop[c];
+        entry_s[J] = (uint16_t)c;
+        for (int j = J; j >= 1; --j) {
+            c -= hop[(size_t)j * S_pad + c];
+            entry_s[j - 1] = (uint16_t)c;
+        }
+        idx_s[0] = 0;
+    }
+    __syncthreads();
+    // level 2: independent 32-row walks, one per thread
+    for (int j = tid; j <= J; j += kThreads) {
+        const int y_lo = kCheck * j + 1;
+        int y_top = kCheck * j + kCheck;
+        int cur;
+        if (y_top <= y_last) {
+            cur = entry_s[j + 1];
+        } else {
+            y_top = y_last;
+            cur = t_x - 1;
+        }
+        for (int y = y_top; y >= y_lo; --y) {
+            idx_s[y] = (uint16_t)cur;
+            const int q = cur / C;
+            const uint32_t wd = bits[(size_t)y * WPR + (q >> 5) * C + (cur - q * C)];
+            cur -= (wd >> (q & 31)) & 1u;
+        }
+    }
+    for (int x = tid; x < S_pad; x += kThreads) end_s[x] = -1;
+    __syncthreads();
+
+    // =================== outputs ===================
+    for (int y = tid; y < t_y; y += kThreads) {
+        const int c = idx_s[y];
+        store_one(path_b, (size_t)y * S + c, p.path_dtype);
+        if (y == y_last || idx_s[y + 1] != c) end_s[c] = y;
+    }
+    if (p.idx) {
+        for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = (y < t_y) ? (int)idx_s[y] : -1;
+    }
+    if (p.status && tid == 0) p.status[b] = MAS_UTT_OK;
+    if (p.dur) {
+        __syncthreads();
+        for (int x = tid; x < S; x += kThreads) {
+            int d = 0;
+            if (x < t_x) d = end_s[x] - (x > 0 ? end_s[x - 1] : -1);
+            p.dur[(size_t)b * S + x] = d;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// lengths from the dense mask (reference __init__.py:16-17)
+// ---------------------------------------------------------------------------
+__global__ void mas_lengths_kernel(const float *__restrict__ mask, int32_t *t_ys, int32_t *t_xs, int T, int S)
+{
+    const int b = blockIdx.x;
+    const float *m = mask + (size_t)b * T * S;
+    float sy = 0.f, sx = 0.f;
+    for (int y = threadIdx.x; y < T; y += blockDim.x) sy += m[(size_t)y * S];
+    for (int x = threadIdx.x; x < S; x += blockDim.x) sx += m[x];
+    __shared__ float red[2][32];
+    for (int o = 16; o > 0; o >>= 1) {
+        sy += __shfl_xor_sync(kFullMask, sy, o);
+        sx += __shfl_xor_sync(kFullMask, sx, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sy;
+        red[1][threadIdx.x >> 5] = sx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ty = 0.f, tx = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+            ty += red[0][i];
+            tx += red[1][i];
+        }
+        t_ys[b] = (int32_t)ty;  // masks are 0/1, sums are exact integers
+        t_xs[b] = (int32_t)tx;
+    }
+}
+
+// longest-first launch order (length bucketing): rank by t_y descending, stable
+__global__ void mas_order_kernel(const int32_t *__restrict__ t_ys, int32_t *order, int B)
+{
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const int mine = t_ys[b];
+        int rank = 0;
+        for (int o = 0; o < B; ++o) {
+            const int other = t_ys[o];
+            rank += (other > mine) || (other == mine && o < b);
+        }
+        order[rank] = b;
+    }
+}
+
+// compact idx [B,T] -> dense path (multi-GPU re-expansion)
+__global__ void mas_expand_kernel(const int32_t *__restrict__ idx, unsigned char *path, int path_dtype, int T, int S)
+{
+    const size_t row = blockIdx.x;  // b*T + y
+    const int c = idx[row];
+    const int esize = path_elem_size(path_dtype);
+    unsigned char *prow = path + row * (size_t)S * esize;
+    const uint32_t one = path_one_bits(path_dtype);
+    if (esize == 4) {
+        uint32_t *q = reinterpret_cast<uint32_t *>(prow);
+        for (int x = threadIdx.x; x < S; x += blockDim.x) q[x] = (x == c) ? one : 0u;
+    } else {
+        uint16_t *q = reinterpret_cast<uint16_t *>(prow);
+        for (int x = threadIdx.x; x < S; x += blockDim.x) q[x] = (x == c) ? (uint16_t)one : (uint16_t)0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host entry points used by mas_api.cu
+// ---------------------------------------------------------------------------
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+size_t dp_workspace_bytes(int B, int T, int S)
+{
+    DpPlan pl{};
+    if (!make_plan(pl, B, T, S, env_int("MAS_DP_ROWS", 0))) return 0;
+    return align_up((size_t)B * 4, 256) + align_up(pl.ws_bits_bytes, 256) + align_up(pl.ws_hop_bytes, 256);
+}
+
+template <int C>
+static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
+{
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MAS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != configured_dev) {
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kSmemBudget));
+        configured_dev = dev;
+    }
+    mas_dp_kernel<C><<<pl.p.B, kThreads, pl.smem_bytes, stream>>>(pl.p);
+    note_launch();
+    MAS_CUDA_TRY(cudaGetLastError());
+    return MAS_OK;
+}
+
+int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
+              int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace, size_t workspace_bytes, int B,
+              int T, int S, cudaStream_t stream)
+{
+    DpPlan pl{};
+    if (!make_plan(pl, B, T, S, env_int("MAS_DP_ROWS", 0))) return MAS_ERR_UNSUPPORTED_SHAPE;
+    const size_t need = dp_workspace_bytes(B, T, S);
+    if (need && (!workspace || workspace_bytes < need)) return MAS_ERR_WORKSPACE;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    DpParams &p = pl.p;
+    p.neg_cent = neg_cent;
+    p.t_ys = t_ys;
+    p.t_xs = t_xs;
+    p.path = static_cast<unsigned char *>(path_out);
+    p.dur = dur_out;
+    p.idx = idx_out;
+    p.status = status_out;
+    p.B = B;
+    p.T = T;
+    p.S = S;
+    p.path_dtype = path_dtype;
+    int32_t *order = reinterpret_cast<int32_t *>(ws);
+    ws += align_up((size_t)B * 4, 256);
+    p.bits_ws = reinterpret_cast<uint32_t *>(ws);
+    ws += align_up(pl.ws_bits_bytes, 256);
+    p.hop_ws = ws;
+    // Length bucketing: when the batch is more than one wave of CTAs, launch the
+    // longest utterances first so short ones fill in behind them.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (B > sms) {
+        mas_order_kernel<<<(B + 255) / 256, 256, 0, stream>>>(t_ys, order, B);
+        note_launch();
+        MAS_CUDA_TRY(cudaGetLastError());
+        p.order = order;
+    } else {
+        p.order = nullptr;
+    }
+    switch (pl.C) {
+        case 1: return launch_dp_c<1>(pl, stream);
+        case 2: return launch_dp_c<2>(pl, stream);
+        case 3: return launch_dp_c<3>(pl, stream);
+        case 4: return launch_dp_c<4>(pl, stream);
+        case 5: return launch_dp_c<5>(pl, stream);
+        case 6: return launch_dp_c<6>(pl, stream);
+        case 7: return launch_dp_c<7>(pl, stream);
+        case 8: return launch_dp_c<8>(pl, stream);
+    }
+    return MAS_ERR_UNSUPPORTED_SHAPE;
+}
+
+int lengths_launch(const float *mask, int32_t *t_ys, int32_t *t_xs, int B, int T, int S, cudaStream_t stream)
+{
+    mas_lengths_kernel<<<B, 256, 0, stream>>>(mask, t_ys, t_xs, T, S);
+    note_launch();
+    MAS_CUDA_TRY(cudaGetLastError());
+    return MAS_OK;
+}
+
+int expand_launch(const int32_t *idx, void *path_out, int path_dtype, int B, int T, int S, cudaStream_t stream)
+{
+    mas_expand_kernel<<<(unsigned)((size_t)B * T), 128, 0, stream>>>(idx, static_cast<unsigned char *>(path_out),
+                                                                      path_dtype, T, S);
+    note_launch();
+    MAS_CUDA_TRY(cudaGetLastError());
+    return MAS_OK;
+}
+
+}  // namespace mas

@@ -1,0 +1,70 @@
+"""Multi-GPU side of the path: the batch shards across
+ranks with no data-path collective; only when the caller wants the global
+result are the COMPACT forms (idx [B,T] int32, durations [B,S] int32)
+all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests) and re-expanded
+locally.  The dense [B,T,S] path is never communicated.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_bounds(batch: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of a batch for `rank`; sizes differ by at most one."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_compact(idx: torch.Tensor, dur: torch.Tensor, batch: int, group=None):
+    """All-gather per-rank compact results into global [batch, T] / [batch, S].
+    Ragged shards are padded to the largest shard for the collective."""
+    world = dist.get_world_size(group)
+    per = (batch + world - 1) // world
+    T, S = idx.shape[1], dur.shape[1]
+    packed = torch.full((per, T + S), -1, dtype=torch.int32, device=idx.device)
+    n = idx.shape[0]
+    packed[:n, :T] = idx
+    packed[:n, T:] = dur
+    out = torch.empty((world * per, T + S), dtype=torch.int32, device=idx.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    rows = []
+    for r in range(world):
+        lo, hi = shard_bounds(batch, r, world)
+        rows.append(out[r * per: r * per + (hi - lo)])
+    full = torch.cat(rows, 0)
+    return full[:, :T].contiguous(), full[:, T:].contiguous()
+
+
+def expand_path(idx: torch.Tensor, S: int, dtype=torch.float32) -> torch.Tensor:
+    """Compact idx [B,T] (-1 = padding row) -> dense {0,1} path [B,T,S] on the GPU."""
+    _lib.require_cuda(idx, "idx")
+    B, T = idx.shape
+    idx = idx.to(torch.int32).contiguous()
+    kdtype = dtype if dtype in _lib.PATH_DTYPES else torch.float32
+    with torch.cuda.device(idx.device):
+        path = torch.empty((B, T, S), dtype=kdtype, device=idx.device)
+        rc = _lib.lib().mas_expand_path(_lib.ptr(idx), _lib.ptr(path), _lib.PATH_DTYPES[kdtype], B, T, S,
+                                        _lib.stream_ptr(idx.device))
+    _lib.check(rc, "mas_expand_path")
+    return path if kdtype == dtype else path.to(dtype)
+
+
+def align_sharded(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=None, *, gather: bool = False,
+                  global_batch=None, group=None):
+    """Align this rank's shard (inputs are already the rank's shard, as under DDP
+    with DistributedBucketSampler, data_utils.py:514).  With gather=True also
+    returns the global (idx, durations) all-gathered in compact form."""
+    from .align import align
+
+    attn, w, (idx, dur, status) = align(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale, noise,
+                                        return_compact=True)
+    if not gather:
+        return attn, w
+    world = dist.get_world_size(group)
+    batch = global_batch if global_batch is not None else idx.shape[0] * world
+    g_idx, g_dur = gather_compact(idx, dur, batch, group)
+    return attn, w, g_idx, g_dur
