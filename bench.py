@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- MAS alignments/sec for the fused neg_cent + maximum_path hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+A step is one pass of the hot path over one batch of synthetic input:
+BASELINE.json configs[1] -- fused neg_cent + MAS, B=64, T_text=256, T_mel=1024,
+192-channel prior -- per GPU (weak scaling: every rank aligns its own B=64 shard,
+no data-path collective).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, S, T, D = 64, 256, 1024, 192
+METRIC = "MAS alignments/sec (B=64,T_text=256,T_mel=1024)"
+UNIT = "alignments/s"
+# algorithmic bytes / flops per alignment
+FUSED_BYTES = 4 * D * T + 2 * 4 * D * S + 4 * T * S        # read z_p, m_p, logs_p; write dense fp32 path
+MAS_BYTES = 2 * 4 * T * S                                   # read neg_cent, write path
+COST_BYTES = 4 * D * T + 2 * 4 * D * S + 4 * T * S          # read z_p, m_p, logs_p; write neg_cent
+COST_FLOPS = 4 * T * S * D                                  # two K=D contractions
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch through the C ABI every step instead of graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# the reference's CPU path (oracle/_ref when it was compiled, else the C port)
+# --------------------------------------------------------------------------
+def cpu_reference_step(inputs):
+    """models.py:1224-1256 on the host, as the reference runs it without a GPU:
+    torch CPU ops for neg_cent (all threads) + the Cython kernel (serial as shipped)."""
+    import torch
+    from oracle import mas_oracle
+
+    z_p, m_p, logs_p, x_mask, y_mask = inputs
+    with torch.no_grad():
+        nc = mas_oracle.neg_cent_torch(z_p, m_p, logs_p)
+        mask = (x_mask.unsqueeze(2) * y_mask.unsqueeze(-1)).squeeze(1)          # models.py:1249
+        values = nc.numpy().astype("float32")                                    # __init__.py:13
+        t_ys = mask.sum(1)[:, 0].numpy().astype("int32")                         # __init__.py:16
+        t_xs = mask.sum(2)[:, 0].numpy().astype("int32")                         # __init__.py:17
+        if mas_oracle.ref_core() is not None:
+            path = mas_oracle.ref_maximum_path_c(values, t_ys, t_xs)
+        else:
+            path = mas_oracle.maximum_path_c(values, t_ys, t_xs)
+        attn = torch.from_numpy(path).to(dtype=nc.dtype)
+        w = attn.sum(1)                                                          # models.py:1256
+    return w
+
+
+def cpu_kind():
+    from oracle import mas_oracle
+
+    return "reference" if mas_oracle.ref_core() is not None else "port"
+
+
+def time_cpu(inputs, reps: int):
+    import torch
+
+    cpu_reference_step(inputs)  # warm
+    best = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(inputs)
+        best.append(time.perf_counter() - t0)
+    mean = sum(best) / len(best)
+    return B / mean, mean, torch.get_num_threads()
+
+
+def make_inputs(seed: int):
+    from torch_tts_b200 import synthetic
+
+    t_x, t_y = synthetic.full_lengths(B, S, T)
+    z_p, m_p, logs_p, x_mask, y_mask = synthetic.prior_inputs(B, S, T, t_x, t_y, D, seed=seed)
+    return (z_p, m_p, logs_p, x_mask, y_mask), t_x, t_y
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    inputs, _, _ = make_inputs(0)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_step(inputs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(inputs)
+    dt = time.perf_counter() - t0
+    value = B * args.steps / dt
+    threads = torch.get_num_threads()
+    sample = f"{args.steps} passes over one full B={B} batch (torch CPU neg_cent on {threads} threads + serial Cython MAS)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fused neg_cent+MAS, B=64, T_text=256, T_mel=1024, D=192 (BASELINE configs[1])",
+                   "host": "reference CPU path, rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": cpu_kind(), "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import torch_tts_b200 as tts
+    from torch_tts_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    # ---- inputs: NSETS rotating buffer sets so consecutive steps never reuse L2-resident data
+    NSETS = 3
+    host_sets, dev_sets = [], []
+    for i in range(NSETS):
+        (z_p, m_p, logs_p, x_mask, y_mask), t_x, t_y = make_inputs(rank * 100 + i)
+        host_sets.append(tuple(t.pin_memory() for t in (z_p, m_p, logs_p, t_y, t_x)))
+        dev_sets.append(tuple(t.to(dev) for t in (z_p, m_p, logs_p, t_y, t_x)))
+    cpu_inputs = (z_p, m_p, logs_p, x_mask, y_mask)
+    plans = [tts.AlignPlan(B, D, T, S, dev) for _ in range(NSETS)]   # separate outputs + workspace per set
+    use_graph = not args.no_graph
+    L.mas_take_launch_count()
+    plans[0].run(*dev_sets[0])
+    torch.cuda.synchronize()
+    launches_per_step = L.mas_take_launch_count()
+    if use_graph:
+        for i in range(NSETS):
+            plans[i].capture(0, *dev_sets[i])
+
+    def step(i):
+        k = i % NSETS
+        if use_graph:
+            plans[k].replay(0)
+        else:
+            plans[k].run(*dev_sets[k])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel timing on the same stream (dominant kernel -> roofline)
+    kern = {}
+    nc_buf = torch.empty((B, T, S), dtype=torch.float32, device=dev)
+    reps = max(10, min(args.steps, 30))
+
+    def time_calls(fn):
+        for _ in range(3):
+            fn(0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    st = torch.cuda.current_stream(dev).cuda_stream
+    cost_ws = torch.empty(L.mas_neg_cent_workspace_bytes(B, D, T, S), dtype=torch.uint8, device=dev)
+    dp_ws = torch.empty(max(L.mas_maximum_path_workspace_bytes(B, T, S), 256), dtype=torch.uint8, device=dev)
+    nc_sets = [torch.empty((B, T, S), dtype=torch.float32, device=dev) for _ in range(NSETS)]
+
+    def cost_fn(i):
+        k = i % NSETS
+        z, m, l, _, _ = dev_sets[k]
+        L.mas_neg_cent_f32(z.data_ptr(), m.data_ptr(), l.data_ptr(), nc_sets[k].data_ptr(), None, cost_ws.data_ptr(),
+                           cost_ws.numel(), B, D, T, S, st)
+
+    def dp_fn(i):
+        k = i % NSETS
+        _, _, _, ty, tx = dev_sets[k]
+        p = plans[k]
+        L.mas_maximum_path_f32(nc_sets[k].data_ptr(), ty.data_ptr(), tx.data_ptr(), p.path.data_ptr(), 0,
+                               p.dur.data_ptr(), p.idx.data_ptr(), p.status.data_ptr(), dp_ws.data_ptr(),
+                               dp_ws.numel(), B, T, S, st)
+
+    kern["neg_cent_ms"] = time_calls(cost_fn)
+    kern["maximum_path_ms"] = time_calls(dp_fn)
+    del nc_buf
+
+    # ---- end to end: pinned host buffers -> H2D -> align -> D2H of durations + compact path
+    out_host = torch.empty((B, S + T), dtype=torch.int32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
+    d2h = out_host.numel() * 4
+    stage = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0]) for _ in range(2)]
+
+    def e2e_step(i):
+        hs, ds, p = host_sets[i % NSETS], stage[i % 2], plans[i % NSETS]
+        for h, d_ in zip(hs, ds):
+            d_.copy_(h, non_blocking=True)
+        p.run(*ds)
+        out_host[:, :S].copy_(p.dur, non_blocking=True)
+        out_host[:, S:].copy_(p.idx, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(5, min(args.steps, 20))
+    a.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    b_.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b_)
+
+    times = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = times.tolist()
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, mean, threads = time_cpu(cpu_inputs, reps=20)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": cpu_kind(),
+               "sample": f"20 passes over one full B={B} batch ({mean * 1e3:.1f} ms each): torch CPU neg_cent on "
+                         f"{threads} threads + serial Cython MAS as shipped; host has {os.cpu_count()} cpus"}
+
+    if rank == 0:
+        hbm, bf16, how = peaks()
+        if kern["neg_cent_ms"] >= kern["maximum_path_ms"]:
+            t_s = kern["neg_cent_ms"] * 1e-3
+            ach = COST_FLOPS * B / t_s / 1e12
+            roof = {"kernel": "neg_cent contraction", "bound": "tensor", "achieved": ach, "peak": bf16,
+                    "unit": "TFLOP/s", "frac": ach / bf16, "traffic": None, "peak_source": how + " (dense bf16 cuBLAS)"}
+        else:
+            t_s = kern["maximum_path_ms"] * 1e-3
+            ach = MAS_BYTES * B / t_s / 1e9
+            roof = {"kernel": "mas_dp_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                    "frac": ach / hbm, "traffic": None, "peak_source": how}
+        step_s = ms * 1e-3 / args.steps
+        fused = {"bound": "hbm", "achieved": FUSED_BYTES * B / step_s / 1e9, "peak": hbm, "unit": "GB/s"}
+        fused["frac"] = fused["achieved"] / hbm
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "fused neg_cent+MAS, B=64 per GPU, T_text=256, T_mel=1024, D=192 (BASELINE configs[1])",
+                       "parallelism": f"dp{world} (batch-sharded, no data-path collective)",
+                       "l2": f"{NSETS} rotating input/output buffer sets (~{NSETS * 190} MB) > 126 MB L2",
+                       "launch": "cuda-graph replay" if use_graph else "C-ABI call per step"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks, "roofline": roof, "roofline_whole_step": fused, "kernels_ms": kern,
+            "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

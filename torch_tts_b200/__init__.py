@@ -12,3 +12,4 @@ __all__ = [
     "maximum_path", "maximum_path_compact", "lengths_from_mask", "align", "neg_cent",
     "shard_bounds", "gather_compact", "expand_path", "align_sharded",
 ]
+from .plan import AlignPlan  # noqa: F401,E402

@@ -31,6 +31,7 @@ constexpr int kThreads = kDpThreads + 32;  // + producer warp
 constexpr int kStages = 8;
 constexpr int kCheck = 32;  // checkpoint interval (rows)
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kZeroBytes = 8192;  // zeroed shared buffer the path zero-fill bulk-stores from
 
 struct DpParams {
     const float *neg_cent;
@@ -47,7 +48,7 @@ struct DpParams {
     int R;  // mel rows per chunk: 4, 8, 16 or 32
     int path_dtype;
     int bits_in_smem, hop_in_smem;
-    uint32_t off_bits, off_hop, off_stage, stage_bytes, off_bnd_v, off_bnd_o, off_idx, off_end, off_entry, off_bar;
+    uint32_t off_bits, off_hop, off_stage, stage_bytes, off_bnd_v, off_bnd_o, off_idx, off_end, off_entry, off_bar, off_zero;
     unsigned long long bits_words_per_cta, hop_bytes_per_cta;
 };
 
@@ -80,9 +81,11 @@ static bool plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, boo
     p.off_stage = (uint32_t)off;
     off += (size_t)kStages * p.stage_bytes;
     p.off_bnd_v = (uint32_t)off;
-    off += (size_t)(kDpWarps - 1) * 4 * R * 4;
+    off += (size_t)(kDpWarps + 1) * 2 * R * 4;
     p.off_bnd_o = (uint32_t)off;
-    off += (size_t)(kDpWarps - 1) * 4 * R * 4;
+    off += (size_t)(kDpWarps + 1) * 2 * R * 4;
+    p.off_zero = (uint32_t)off;
+    off += kZeroBytes;
     p.off_idx = (uint32_t)off;
     off += align_up((size_t)T * 2, 16);
     p.off_end = (uint32_t)off;
@@ -143,46 +146,151 @@ __device__ __forceinline__ void store_one(unsigned char *path_b, size_t cell, in
         reinterpret_cast<uint16_t *>(path_b)[cell] = (uint16_t)path_one_bits(path_dtype);
 }
 
-// One mel row of the forward DP for this thread's C columns.
-//   v/org: running DP row and checkpoint origin per column (registers)
-//   cost:  neg_cent[y, x0..x0+C)
-//   left_v/left_o: value/origin of column x0-1 (used by lane 0 only)
-// Returns in `words` the ballot of the backtrack decision per column slot.
-template <int C, bool kEdge>
-__device__ __forceinline__ void dp_row(float (&v)[C], int (&org)[C], const float (&cost)[C], float left_v,
-                                       int left_o, int y, int x0, int lane, bool col0, uint32_t (&words)[C])
+// NR mel rows (4 in the main loop, 1 for the tail) of the forward DP for this
+// thread's C consecutive columns.
+//   v/org   running DP row and checkpoint origin per column (registers)
+//   trow    &tile[r * S + x0]: this thread's first cost of the first row
+//   carry   value/origin of column x0-1 after the previous row (lane 0 only matters)
+//   bin_*   boundary ring written by the warp to the left, slot of row y
+//   bout_*  this warp's boundary ring, slot of row y (lane 31 writes)
+//   brow    direction words of row y for this warp (lane 0 writes)
+template <int C, int NR, bool kEdge, bool kVec>
+__device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], const float *trow, int S, float &carry_v,
+                                        int &carry_o, const float *bin_v, const int *bin_o, float *bout_v,
+                                        int *bout_o, uint32_t *brow, int y, int x0, int lane)
 {
-    float up_v = __shfl_up_sync(kFullMask, v[C - 1], 1);
-    int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
-    if (lane == 0) {
-        up_v = left_v;
-        up_o = left_o;
-    }
+    constexpr int WPR = kDpWarps * C;
+    float cost[NR][C];
+    float lv[NR + 1];
+    int lo[NR + 1];
+    lv[0] = carry_v;
+    lo[0] = carry_o;
+    // ---- all loads for the NR rows up front
 #pragma unroll
-    for (int k = C - 1; k >= 0; --k) {
-        const float v_prev = (k == 0) ? up_v : v[k - 1];  // value[y-1, x-1]  (core.pyx:21-27)
-        const int o_prev = (k == 0) ? up_o : org[k - 1];
-        const float v_cur = v[k];                          // value[y-1, x]    (core.pyx:17-20)
-        // Cython's max(v_prev, v_cur): (v_cur > v_prev) ? v_cur : v_prev
-        const float m = (v_cur > v_prev) ? v_cur : v_prev;
-        // backtrack rule core.pyx:32: index != 0 and (index == y or value[y-1,x] < value[y-1,x-1])
-        bool diag = v_cur < v_prev;
-        if (kEdge) diag = diag || (x0 + k == y);
-        if (k == 0) diag = diag && !col0;
-        float nv = cost[k] + m;  // core.pyx:28
-        int no = diag ? o_prev : org[k];
-        if (kEdge) {
-            const bool in_band = (x0 + k <= y);  // upper band edge, core.pyx:16
-            nv = in_band ? nv : v_cur;
-            no = in_band ? no : org[k];
+    for (int i = 0; i < NR; ++i) {
+        const float *src = trow + (size_t)i * S;
+        if (kVec && (C % 4 == 0)) {
+#pragma unroll
+            for (int k = 0; k < C; k += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(src + k);
+                cost[i][k] = t.x, cost[i][k + 1] = t.y, cost[i][k + 2] = t.z, cost[i][k + 3] = t.w;
+            }
+        } else if (kVec && (C % 2 == 0)) {
+#pragma unroll
+            for (int k = 0; k < C; k += 2) {
+                const float2 t = *reinterpret_cast<const float2 *>(src + k);
+                cost[i][k] = t.x, cost[i][k + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < C; ++k) cost[i][k] = src[k];
         }
-        v[k] = nv;
-        org[k] = no;
-        words[k] = __ballot_sync(kFullMask, diag);
+    }
+    if (NR == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(bin_v);
+        const int4 u = *reinterpret_cast<const int4 *>(bin_o);
+        lv[1] = t.x, lv[2] = t.y, lv[3] = t.z, lv[4] = t.w;
+        lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            lv[i + 1] = bin_v[i];
+            lo[i + 1] = bin_o[i];
+        }
+    }
+    float ov[NR];
+    int oo[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        float up_v = __shfl_up_sync(kFullMask, v[C - 1], 1);
+        int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
+        if (lane == 0) {
+            up_v = lv[i];
+            up_o = lo[i];
+        }
+        uint32_t words[C];
+#pragma unroll
+        for (int k = C - 1; k >= 0; --k) {
+            const float v_prev = (k == 0) ? up_v : v[k - 1];  // value[y-1, x-1]  (core.pyx:21-27)
+            const int o_prev = (k == 0) ? up_o : org[k - 1];
+            const float v_cur = v[k];                          // value[y-1, x]    (core.pyx:17-20)
+            // Cython's max(v_prev, v_cur) is (v_cur > v_prev) ? v_cur : v_prev
+            const float m = (v_cur > v_prev) ? v_cur : v_prev;
+            // backtrack rule, core.pyx:32: index == y or value[y-1,x] < value[y-1,x-1]
+            // (the "index != 0" guard is applied by the backtrack itself)
+            bool diag = v_cur < v_prev;
+            if (kEdge) diag = diag || (x0 + k == y + i);
+            float nv = cost[i][k] + m;  // core.pyx:28
+            int no = diag ? o_prev : org[k];
+            if (kEdge) {
+                const bool in_band = (x0 + k <= y + i);  // upper band edge, core.pyx:16
+                nv = in_band ? nv : v_cur;
+                no = in_band ? no : org[k];
+            }
+            v[k] = nv;
+            org[k] = no;
+            words[k] = __ballot_sync(kFullMask, diag);
+        }
+        ov[i] = v[C - 1];
+        oo[i] = org[C - 1];
+        if (lane == 0) {
+            uint32_t *dst = brow + (size_t)i * WPR;
+            if (C == 2) {
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(words[0], words[1]);
+            } else if (C == 4) {
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < C; ++k) dst[k] = words[k];
+            }
+        }
+    }
+    if (lane == 31) {
+        if (NR == 4) {
+            *reinterpret_cast<float4 *>(bout_v) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            *reinterpret_cast<int4 *>(bout_o) = make_int4(oo[0], oo[1], oo[2], oo[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                bout_v[i] = ov[i];
+                bout_o[i] = oo[i];
+            }
+        }
+    }
+    carry_v = lv[NR];
+    carry_o = lo[NR];
+}
+
+template <int C, bool kEdge, bool kVec>
+__device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], const float *tile, int S, int rows, int row0,
+                                         int ring_mask, float &carry_v, int &carry_o, const float *bin_v,
+                                         const int *bin_o, float *bout_v, int *bout_o, uint32_t *bits_w, int x0,
+                                         int lane)
+{
+    constexpr int WPR = kDpWarps * C;
+    const float *trow = tile + x0;
+    uint32_t *brow = bits_w + (size_t)row0 * WPR;
+    int r = 0;
+    for (; r + 4 <= rows; r += 4) {
+        const int slot = (row0 + r) & ring_mask;
+        dp_rows<C, 4, kEdge, kVec>(v, org, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
+                                   bout_o + slot, brow, row0 + r, x0, lane);
+        trow += (size_t)4 * S;
+        brow += 4 * WPR;
+    }
+    for (; r < rows; ++r) {
+        const int slot = (row0 + r) & ring_mask;
+        dp_rows<C, 1, kEdge, kVec>(v, org, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
+                                   bout_o + slot, brow, row0 + r, x0, lane);
+        trow += S;
+        brow += WPR;
     }
 }
 
-template <int C>
+// checkpoint row c_j: c_0 = 0, c_j = 32 j - 1
+__device__ __forceinline__ int check_row(int j) { return j == 0 ? 0 : kCheck * j - 1; }
+
+template <int C, bool kVec>
 __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -220,21 +328,30 @@ __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
     uint32_t *bits = p.bits_in_smem ? reinterpret_cast<uint32_t *>(smem + p.off_bits)
                                     : p.bits_ws + (size_t)blockIdx.x * p.bits_words_per_cta;
     unsigned char *hop = p.hop_in_smem ? (smem + p.off_hop) : p.hop_ws + (size_t)blockIdx.x * p.hop_bytes_per_cta;
-    float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);
+    float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);  // [kDpWarps + 1][2R]
     int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
     uint16_t *idx_s = reinterpret_cast<uint16_t *>(smem + p.off_idx);
     int *end_s = reinterpret_cast<int *>(smem + p.off_end);
     uint16_t *entry_s = reinterpret_cast<uint16_t *>(smem + p.off_entry);
+    unsigned char *zero_s = smem + p.off_zero;
 
+    const int ring = 2 * R;
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
     }
+    // ring 0 stands in for "the warp left of warp 0": column -1 is the -1e9 sentinel (core.pyx:24)
+    for (int i = tid; i < ring; i += kThreads) {
+        bnd_v[i] = kNeg;
+        bnd_o[i] = 0;
+    }
+    for (int i = tid; i < kZeroBytes / 16; i += kThreads) reinterpret_cast<uint4 *>(zero_s)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();  // zero_s is read by the bulk-store engine
     __syncthreads();
 
     const int n_chunks = (t_y + R - 1) / R;
     const int n_steps = n_chunks + kDpWarps - 1;
-    const int ring_mask = 4 * R - 1;
+    const int ring_mask = ring - 1;
     const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
     const size_t total_bytes = (size_t)p.B * plane * 4;
 
@@ -263,23 +380,35 @@ __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
             const int pre = min(kStages, n_chunks);
             for (int c = 0; c < pre; ++c) issue_tile(c);
         }
-        // zero-fill of the dense path, spread over the chunk steps
+        // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
+        // zeroed shared buffer when the plane is 16-byte aligned, plain stores otherwise
         const size_t pbytes = plane * esize;
+        const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
         const size_t quota = align_up((pbytes + n_steps - 1) / n_steps, 512);
         for (int step = 0; step < n_steps; ++step) {
             size_t lo = (size_t)step * quota, hi = lo + quota;
             if (lo > pbytes) lo = pbytes;
             if (hi > pbytes || step == n_steps - 1) hi = pbytes;
-            if (hi > lo) zero_bytes_warp(path_b + lo, hi - lo, lane);
+            if (hi > lo) {
+                if (bulk_ok) {
+                    if (lane == 0) {
+                        for (size_t o = lo; o < hi; o += kZeroBytes)
+                            bulk_s2g(path_b + o, zero_s, (uint32_t)min((size_t)kZeroBytes, hi - o));
+                        bulk_commit();
+                    }
+                } else {
+                    zero_bytes_warp(path_b + lo, hi - lo, lane);
+                }
+            }
             __syncthreads();
             const int freed = step - (kDpWarps - 1);
             if (lane == 0 && freed >= 0 && freed + kStages < n_chunks) issue_tile(freed + kStages);
         }
+        if (bulk_ok && lane == 0) bulk_wait_all();  // zeros have landed before the ones are scattered
     } else {
         // =================== DP warps ===================
         const int w = warp;
         const int x0 = (w * 32 + lane) * C;
-        const bool col0 = (x0 == 0);
         float v[C];
         int org[C];
 #pragma unroll
@@ -287,63 +416,40 @@ __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
             v[k] = kNeg;
             org[k] = x0 + k;
         }
+        // value left of column x0 for the first row: 0 for column 0 at y == 0 (core.pyx:22-23)
+        float carry_v = (w == 0) ? 0.0f : kNeg;
+        int carry_o = 0;
+        const float *bin_v = bnd_v + (size_t)w * ring;
+        const int *bin_o = bnd_o + (size_t)w * ring;
+        float *bout_v = bnd_v + (size_t)(w + 1) * ring;
+        int *bout_o = bnd_o + (size_t)(w + 1) * ring;
+        uint32_t *bits_w = bits + w * C;
+        const int edge_rows = (w + 1) * 32 * C;  // rows where some column of this warp is still above the diagonal
         for (int step = 0; step < n_steps; ++step) {
             const int c = step - w;
             if (c >= 0 && c < n_chunks) {
                 const int row0 = c * R;
                 const int rows = min(R, t_y - row0);
-                const uint32_t mis = (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
+                const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
                 const float *tile = reinterpret_cast<const float *>(smem + p.off_stage +
                                                                     (size_t)(c % kStages) * p.stage_bytes + mis);
                 mbar_wait(&full[c % kStages], (uint32_t)(c / kStages) & 1u);
-                const bool edge = row0 < S_pad;
-                // checkpoint rows are multiples of 32 and R divides 32 (or is 32): only a chunk's row 0 can be one
-                for (int r = 0; r < rows; r += 4) {
-                    float cost[4][C];
-                    float lv[4];
-                    int lo[4];
+                if (row0 < edge_rows)
+                    dp_chunk<C, true, kVec>(v, org, tile, S, rows, row0, ring_mask, carry_v, carry_o, bin_v, bin_o,
+                                            bout_v, bout_o, bits_w, x0, lane);
+                else
+                    dp_chunk<C, false, kVec>(v, org, tile, S, rows, row0, ring_mask, carry_v, carry_o, bin_v, bin_o,
+                                             bout_v, bout_o, bits_w, x0, lane);
+                // checkpoint after rows 31, 63, ...: remember where each column backtracks to, restart origins
+                if (((row0 + rows) & (kCheck - 1)) == 0) {
+                    unsigned char *hrow = hop + (size_t)((row0 + rows) / kCheck) * S_pad;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (r + i < rows) {
-#pragma unroll
-                            for (int k = 0; k < C; ++k) cost[i][k] = tile[(size_t)(r + i) * S + x0 + k];
-                        }
-                        const int y = row0 + r + i;
-                        if (w == 0) {
-                            lv[i] = (y == 0) ? 0.0f : kNeg;  // core.pyx:21-25
-                            lo[i] = 0;
-                        } else {
-                            lv[i] = bnd_v[(w - 1) * 4 * R + (y & ring_mask)];
-                            lo[i] = bnd_o[(w - 1) * 4 * R + (y & ring_mask)];
-                        }
+                    for (int k = 0; k < C; ++k) {
+                        hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                        org[k] = x0 + k;
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (r + i < rows) {
-                            const int y = row0 + r + i;
-                            uint32_t words[C];
-                            if (edge)
-                                dp_row<C, true>(v, org, cost[i], lv[i], lo[i], y, x0, lane, col0, words);
-                            else
-                                dp_row<C, false>(v, org, cost[i], lv[i], lo[i], y, x0, lane, col0, words);
-                            if (lane == 0) {
-#pragma unroll
-                                for (int k = 0; k < C; ++k) bits[(size_t)y * WPR + w * C + k] = words[k];
-                            }
-                            if (((y & (kCheck - 1)) == 0) && y > 0) {
-                                unsigned char *hrow = hop + (size_t)(y / kCheck) * S_pad;
-#pragma unroll
-                                for (int k = 0; k < C; ++k) {
-                                    hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
-                                    org[k] = x0 + k;
-                                }
-                            }
-                            if (w < kDpWarps - 1 && lane == 31) {
-                                bnd_v[w * 4 * R + ((y + 1) & ring_mask)] = v[C - 1];
-                                bnd_o[w * 4 * R + ((y + 1) & ring_mask)] = org[C - 1];
-                            }
-                        }
-                    }
+                    // the right-hand warp must see the restarted origin of our last column
+                    if (lane == 31) bout_o[(row0 + rows - 1) & ring_mask] = x0 + C - 1;
                 }
             }
             __syncthreads();
@@ -357,25 +463,25 @@ __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
 
     // =================== backtrack ===================
     const int y_last = t_y - 1;
-    const int J = y_last / kCheck;
+    const int J = t_y / kCheck;  // checkpoints stored: after rows 31, 63, ..., 32 J - 1
     if (tid == 0) {
         // level 1: one dependent load per 32 rows
         int c = t_x - 1;
-        c -= hop[c];
+        c -= hop[c];  // column at row c_J
         entry_s[J] = (uint16_t)c;
         for (int j = J; j >= 1; --j) {
-            c -= hop[(size_t)j * S_pad + c];
+            c -= hop[(size_t)j * S_pad + c];  // column at row c_{j-1}
             entry_s[j - 1] = (uint16_t)c;
         }
         idx_s[0] = 0;
     }
     __syncthreads();
-    // level 2: independent 32-row walks, one per thread
+    // level 2: independent walks of <= 32 rows, one per thread
     for (int j = tid; j <= J; j += kThreads) {
-        const int y_lo = kCheck * j + 1;
-        int y_top = kCheck * j + kCheck;
-        int cur;
-        if (y_top <= y_last) {
+        const int y_lo = check_row(j) + 1;
+        int y_top, cur;
+        if (j < J) {
+            y_top = check_row(j + 1);
             cur = entry_s[j + 1];
         } else {
             y_top = y_last;
@@ -385,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
             idx_s[y] = (uint16_t)cur;
             const int q = cur / C;
             const uint32_t wd = bits[(size_t)y * WPR + (q >> 5) * C + (cur - q * C)];
-            cur -= (wd >> (q & 31)) & 1u;
+            cur -= (cur != 0) ? (int)((wd >> (q & 31)) & 1u) : 0;  // core.pyx:32 "index != 0 and ..."
         }
     }
     for (int x = tid; x < S_pad; x += kThreads) end_s[x] = -1;
@@ -489,21 +595,29 @@ size_t dp_workspace_bytes(int B, int T, int S)
     return align_up((size_t)B * 4, 256) + align_up(pl.ws_bits_bytes, 256) + align_up(pl.ws_hop_bytes, 256);
 }
 
-template <int C>
-static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
+template <int C, bool kVec>
+static int launch_dp_cv(const DpPlan &pl, cudaStream_t stream)
 {
     static thread_local int configured_dev = -1;
     int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     if (dev != configured_dev) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kSmemBudget));
         configured_dev = dev;
     }
-    mas_dp_kernel<C><<<pl.p.B, kThreads, pl.smem_bytes, stream>>>(pl.p);
+    mas_dp_kernel<C, kVec><<<pl.p.B, kThreads, pl.smem_bytes, stream>>>(pl.p);
     note_launch();
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;
+}
+
+template <int C>
+static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
+{
+    // vector cost loads need every tile row 16-byte aligned in shared memory
+    const bool vec = (pl.p.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(pl.p.neg_cent) & 15) == 0);
+    return vec ? launch_dp_cv<C, true>(pl, stream) : launch_dp_cv<C, false>(pl, stream);
 }
 
 int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
