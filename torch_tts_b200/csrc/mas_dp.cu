@@ -76,7 +76,7 @@ static bool plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, boo
     if (bits_smem) off += align_up((size_t)T * WPR * 4, 16);
     p.off_hop = (uint32_t)off;
     if (hop_smem) off += align_up((size_t)hop_rows * S_pad, 16);
-    p.stage_bytes = (uint32_t)align_up((size_t)R * S * 4 + 16 + (size_t)(S_pad - S) * 4 + 16, 128);
+    p.stage_bytes = (uint32_t)align_up((size_t)R * S * 4 + 16 + 64, 128);  // tile + misalignment + zeroed pad
     off = align_up(off, 128);
     p.off_stage = (uint32_t)off;
     off += (size_t)kStages * p.stage_bytes;
@@ -154,10 +154,13 @@ __device__ __forceinline__ void store_one(unsigned char *path_b, size_t cell, in
 //   bin_*   boundary ring written by the warp to the left, slot of row y
 //   bout_*  this warp's boundary ring, slot of row y (lane 31 writes)
 //   brow    direction words of row y for this warp (lane 0 writes)
-template <int C, int NR, bool kEdge, bool kVec>
-__device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], const float *trow, int S, float &carry_v,
-                                        int &carry_o, const float *bin_v, const int *bin_o, float *bout_v,
-                                        int *bout_o, uint32_t *brow, int y, int x0, int lane)
+//   kExact  false: max via FMNMX (short dependency chain); exact while every cost is
+//           finite, which `fin` tracks (it turns NaN as soon as one is not).
+//           true: the reference's compare-select, bit-for-bit also for NaN/Inf input.
+template <int C, int NR, bool kEdge, bool kVec, bool kExact>
+__device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float (&fin)[C], const float *trow, int S,
+                                        float &carry_v, int &carry_o, const float *bin_v, const int *bin_o,
+                                        float *bout_v, int *bout_o, uint32_t *brow, int y, int x0, int lane)
 {
     constexpr int WPR = kDpWarps * C;
     float cost[NR][C];
@@ -214,8 +217,15 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], const floa
             const float v_prev = (k == 0) ? up_v : v[k - 1];  // value[y-1, x-1]  (core.pyx:21-27)
             const int o_prev = (k == 0) ? up_o : org[k - 1];
             const float v_cur = v[k];                          // value[y-1, x]    (core.pyx:17-20)
-            // Cython's max(v_prev, v_cur) is (v_cur > v_prev) ? v_cur : v_prev
-            const float m = (v_cur > v_prev) ? v_cur : v_prev;
+            // Cython's max(v_prev, v_cur) is (v_cur > v_prev) ? v_cur : v_prev; with no NaN in
+            // flight that is fmaxf (one FMNMX instead of FSETP -> FSEL on the dependency chain)
+            float m;
+            if (kExact) {
+                m = (v_cur > v_prev) ? v_cur : v_prev;
+            } else {
+                m = fmaxf(v_prev, v_cur);
+                fin[k] = fmaf(cost[i][k], 0.0f, fin[k]);  // NaN iff some cost was NaN or +-Inf
+            }
             // backtrack rule, core.pyx:32: index == y or value[y-1,x] < value[y-1,x-1]
             // (the "index != 0" guard is applied by the backtrack itself)
             bool diag = v_cur < v_prev;
@@ -261,26 +271,31 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], const floa
     carry_o = lo[NR];
 }
 
-template <int C, bool kEdge, bool kVec>
-__device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], const float *tile, int S, int rows, int row0,
+template <int C, bool kEdge, bool kVec, bool kExact>
+__device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float (&fin)[C], const float *tile, int S,
+                                         int rows, int row0,
                                          int ring_mask, float &carry_v, int &carry_o, const float *bin_v,
                                          const int *bin_o, float *bout_v, int *bout_o, uint32_t *bits_w, int x0,
                                          int lane)
 {
     constexpr int WPR = kDpWarps * C;
-    const float *trow = tile + x0;
+    // Threads whose columns lie past S re-read the last real columns instead of whatever
+    // follows the row: their results are never used, but they must not invent NaNs.
+    // (A thread straddling S reads at most C-1 floats of the next row, or of the zeroed
+    // pad the producer keeps behind every tile.)
+    const float *trow = tile + (x0 < S ? x0 : S - C);
     uint32_t *brow = bits_w + (size_t)row0 * WPR;
     int r = 0;
     for (; r + 4 <= rows; r += 4) {
         const int slot = (row0 + r) & ring_mask;
-        dp_rows<C, 4, kEdge, kVec>(v, org, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
+        dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
                                    bout_o + slot, brow, row0 + r, x0, lane);
         trow += (size_t)4 * S;
         brow += 4 * WPR;
     }
     for (; r < rows; ++r) {
         const int slot = (row0 + r) & ring_mask;
-        dp_rows<C, 1, kEdge, kVec>(v, org, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
+        dp_rows<C, 1, kEdge, kVec, kExact>(v, org, fin, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
                                    bout_o + slot, brow, row0 + r, x0, lane);
         trow += S;
         brow += WPR;
@@ -355,108 +370,135 @@ __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
     const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
     const size_t total_bytes = (size_t)p.B * plane * 4;
 
-    if (warp == kDpWarps) {
-        // =================== producer warp ===================
-        auto issue_tile = [&](int c) {
-            const int row0 = c * R;
-            const int rows = min(R, t_y - row0);
-            const size_t start = (utt_elem0 + (size_t)row0 * S) * 4;
-            const uint32_t mis = (uint32_t)(start & 15);
-            const size_t src0 = start - mis;
-            const uint32_t want = mis + (uint32_t)rows * S * 4;
-            uint32_t bulk = (want + 15u) & ~15u;
-            unsigned char *dst = smem + p.off_stage + (size_t)(c % kStages) * p.stage_bytes;
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(p.neg_cent) + src0;
-            if (src0 + bulk > total_bytes) {
-                // the 16-byte round-up would run past the tensor: finish the tail by hand
-                bulk = want & ~15u;
-                for (uint32_t o = bulk; o < want; o += 4)
-                    *reinterpret_cast<float *>(dst + o) = *reinterpret_cast<const float *>(src + o);
-            }
-            mbar_arrive_expect_tx(&full[c % kStages], bulk);
-            if (bulk) bulk_g2s(dst, src, bulk, &full[c % kStages]);
-        };
-        if (lane == 0) {
-            const int pre = min(kStages, n_chunks);
-            for (int c = 0; c < pre; ++c) issue_tile(c);
-        }
-        // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
-        // zeroed shared buffer when the plane is 16-byte aligned, plain stores otherwise
-        const size_t pbytes = plane * esize;
-        const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
-        const size_t quota = align_up((pbytes + n_steps - 1) / n_steps, 512);
-        for (int step = 0; step < n_steps; ++step) {
-            size_t lo = (size_t)step * quota, hi = lo + quota;
-            if (lo > pbytes) lo = pbytes;
-            if (hi > pbytes || step == n_steps - 1) hi = pbytes;
-            if (hi > lo) {
-                if (bulk_ok) {
-                    if (lane == 0) {
-                        for (size_t o = lo; o < hi; o += kZeroBytes)
-                            bulk_s2g(path_b + o, zero_s, (uint32_t)min((size_t)kZeroBytes, hi - o));
-                        bulk_commit();
-                    }
-                } else {
-                    zero_bytes_warp(path_b + lo, hi - lo, lane);
-                }
-            }
-            __syncthreads();
-            const int freed = step - (kDpWarps - 1);
-            if (lane == 0 && freed >= 0 && freed + kStages < n_chunks) issue_tile(freed + kStages);
-        }
-        if (bulk_ok && lane == 0) bulk_wait_all();  // zeros have landed before the ones are scattered
-    } else {
-        // =================== DP warps ===================
-        const int w = warp;
-        const int x0 = (w * 32 + lane) * C;
-        float v[C];
-        int org[C];
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-            v[k] = kNeg;
-            org[k] = x0 + k;
-        }
-        // value left of column x0 for the first row: 0 for column 0 at y == 0 (core.pyx:22-23)
-        float carry_v = (w == 0) ? 0.0f : kNeg;
-        int carry_o = 0;
-        const float *bin_v = bnd_v + (size_t)w * ring;
-        const int *bin_o = bnd_o + (size_t)w * ring;
-        float *bout_v = bnd_v + (size_t)(w + 1) * ring;
-        int *bout_o = bnd_o + (size_t)(w + 1) * ring;
-        uint32_t *bits_w = bits + w * C;
-        const int edge_rows = (w + 1) * 32 * C;  // rows where some column of this warp is still above the diagonal
-        for (int step = 0; step < n_steps; ++step) {
-            const int c = step - w;
-            if (c >= 0 && c < n_chunks) {
+    // Pass 0 runs the short-chain body; only if it met a non-finite cost does pass 1 redo the
+    // forward DP with the reference's exact compare-select (NaN/Inf semantics of core.pyx).
+    for (int pass = 0; pass < 2; ++pass) {
+        const int g0 = pass * n_chunks;  // running tile number: stage = g % kStages, parity = (g / kStages) & 1
+        bool saw_nonfinite = false;
+        if (warp == kDpWarps) {
+            // =================== producer warp ===================
+            auto issue_tile = [&](int c) {
+                const int g = g0 + c;
                 const int row0 = c * R;
                 const int rows = min(R, t_y - row0);
-                const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
-                const float *tile = reinterpret_cast<const float *>(smem + p.off_stage +
-                                                                    (size_t)(c % kStages) * p.stage_bytes + mis);
-                mbar_wait(&full[c % kStages], (uint32_t)(c / kStages) & 1u);
-                if (row0 < edge_rows)
-                    dp_chunk<C, true, kVec>(v, org, tile, S, rows, row0, ring_mask, carry_v, carry_o, bin_v, bin_o,
-                                            bout_v, bout_o, bits_w, x0, lane);
-                else
-                    dp_chunk<C, false, kVec>(v, org, tile, S, rows, row0, ring_mask, carry_v, carry_o, bin_v, bin_o,
-                                             bout_v, bout_o, bits_w, x0, lane);
-                // checkpoint after rows 31, 63, ...: remember where each column backtracks to, restart origins
-                if (((row0 + rows) & (kCheck - 1)) == 0) {
-                    unsigned char *hrow = hop + (size_t)((row0 + rows) / kCheck) * S_pad;
-#pragma unroll
-                    for (int k = 0; k < C; ++k) {
-                        hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
-                        org[k] = x0 + k;
-                    }
-                    // the right-hand warp must see the restarted origin of our last column
-                    if (lane == 31) bout_o[(row0 + rows - 1) & ring_mask] = x0 + C - 1;
+                const size_t start = (utt_elem0 + (size_t)row0 * S) * 4;
+                const uint32_t mis = (uint32_t)(start & 15);
+                const size_t src0 = start - mis;
+                const uint32_t want = mis + (uint32_t)rows * S * 4;
+                uint32_t bulk = (want + 15u) & ~15u;
+                unsigned char *dst = smem + p.off_stage + (size_t)(g % kStages) * p.stage_bytes;
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(p.neg_cent) + src0;
+                // finite pad behind the tile for the one thread whose columns straddle S
+                *reinterpret_cast<uint4 *>(dst + ((want + 15u) & ~15u)) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(dst + ((want + 15u) & ~15u) + 16) = make_uint4(0, 0, 0, 0);
+                if (src0 + bulk > total_bytes) {
+                    // the 16-byte round-up would run past the tensor: finish the tail by hand
+                    bulk = want & ~15u;
+                    for (uint32_t o = bulk; o < ((want + 15u) & ~15u); o += 4)
+                        *reinterpret_cast<float *>(dst + o) =
+                            (o < want) ? *reinterpret_cast<const float *>(src + o) : 0.0f;
                 }
+                mbar_arrive_expect_tx(&full[g % kStages], bulk);
+                if (bulk) bulk_g2s(dst, src, bulk, &full[g % kStages]);
+            };
+            if (lane == 0) {
+                const int pre = min(kStages, n_chunks);
+                for (int c = 0; c < pre; ++c) issue_tile(c);
             }
-            __syncthreads();
-        }
-        // origin of the last row relative to its checkpoint -> hop row 0
+            // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
+            // zeroed shared buffer when the plane is 16-byte aligned, plain stores otherwise
+            const size_t pbytes = (pass == 0) ? plane * esize : 0;
+            const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
+            const size_t quota = align_up((pbytes + n_steps - 1) / n_steps, 512);
+            for (int step = 0; step < n_steps; ++step) {
+                size_t lo = (size_t)step * quota, hi = lo + quota;
+                if (lo > pbytes) lo = pbytes;
+                if (hi > pbytes || step == n_steps - 1) hi = pbytes;
+                if (hi > lo) {
+                    if (bulk_ok) {
+                        if (lane == 0) {
+                            for (size_t o = lo; o < hi; o += kZeroBytes)
+                                bulk_s2g(path_b + o, zero_s, (uint32_t)min((size_t)kZeroBytes, hi - o));
+                            bulk_commit();
+                        }
+                    } else {
+                        zero_bytes_warp(path_b + lo, hi - lo, lane);
+                    }
+                }
+                __syncthreads();
+                const int freed = step - (kDpWarps - 1);
+                if (lane == 0 && freed >= 0 && freed + kStages < n_chunks) issue_tile(freed + kStages);
+            }
+            if (pass == 0 && bulk_ok && lane == 0) bulk_wait_all();  // zeros land before the ones are scattered
+        } else {
+            // =================== DP warps ===================
+            const int w = warp;
+            const int x0 = (w * 32 + lane) * C;
+            float v[C], fin[C];
+            int org[C];
 #pragma unroll
-        for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
+            for (int k = 0; k < C; ++k) {
+                v[k] = kNeg;
+                org[k] = x0 + k;
+                fin[k] = 0.0f;
+            }
+            // value left of column x0 for the first row: 0 for column 0 at y == 0 (core.pyx:22-23)
+            float carry_v = (w == 0) ? 0.0f : kNeg;
+            int carry_o = 0;
+            const float *bin_v = bnd_v + (size_t)w * ring;
+            const int *bin_o = bnd_o + (size_t)w * ring;
+            float *bout_v = bnd_v + (size_t)(w + 1) * ring;
+            int *bout_o = bnd_o + (size_t)(w + 1) * ring;
+            uint32_t *bits_w = bits + w * C;
+            const int edge_rows = (w + 1) * 32 * C;  // rows where a column of this warp is still above the diagonal
+            for (int step = 0; step < n_steps; ++step) {
+                const int c = step - w;
+                if (c >= 0 && c < n_chunks) {
+                    const int g = g0 + c;
+                    const int row0 = c * R;
+                    const int rows = min(R, t_y - row0);
+                    const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
+                    const float *tile = reinterpret_cast<const float *>(smem + p.off_stage +
+                                                                        (size_t)(g % kStages) * p.stage_bytes + mis);
+                    mbar_wait(&full[g % kStages], (uint32_t)(g / kStages) & 1u);
+                    const bool edge = row0 < edge_rows;
+#define MAS_CHUNK(EDGE, EXACT)                                                                                    \
+    dp_chunk<C, EDGE, kVec, EXACT>(v, org, fin, tile, S, rows, row0, ring_mask, carry_v, carry_o, bin_v, bin_o, \
+                                   bout_v, bout_o, bits_w, x0, lane)
+                    if (pass == 0) {
+                        if (edge)
+                            MAS_CHUNK(true, false);
+                        else
+                            MAS_CHUNK(false, false);
+                    } else {
+                        if (edge)
+                            MAS_CHUNK(true, true);
+                        else
+                            MAS_CHUNK(false, true);
+                    }
+#undef MAS_CHUNK
+                    // checkpoint after rows 31, 63, ...: remember where each column backtracks to, restart origins
+                    if (((row0 + rows) & (kCheck - 1)) == 0) {
+                        unsigned char *hrow = hop + (size_t)((row0 + rows) / kCheck) * S_pad;
+#pragma unroll
+                        for (int k = 0; k < C; ++k) {
+                            hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                            org[k] = x0 + k;
+                        }
+                        // the right-hand warp must see the restarted origin of our last column
+                        if (lane == 31) bout_o[(row0 + rows - 1) & ring_mask] = x0 + C - 1;
+                    }
+                }
+                __syncthreads();
+            }
+            // origin of the last row relative to its checkpoint -> hop row 0
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                saw_nonfinite = saw_nonfinite || (fin[k] != fin[k]);
+            }
+        }
+        if (pass == 1 || !__syncthreads_or(saw_nonfinite)) break;
     }
     if (!p.bits_in_smem || !p.hop_in_smem) __threadfence_block();
     __syncthreads();
