@@ -29,7 +29,8 @@ int expand_launch(const int32_t *idx, void *path_out, int path_dtype, int B, int
 // mas_cost.cu
 size_t cost_workspace_bytes(int B, int D, int T, int S);
 int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
-                void *workspace, size_t workspace_bytes, int B, int D, int T, int S, cudaStream_t stream);
+                const int32_t *t_ys, void *workspace, size_t workspace_bytes, int B, int D, int T, int S,
+                cudaStream_t stream);
 int add_noise_launch(const float *nc, const float *noise, const double *stats, float scale, float *out, size_t n,
                      cudaStream_t stream);
 
@@ -121,7 +122,7 @@ int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p, fl
     if (D < 1) return MAS_ERR_BAD_SHAPE;
     if (!aligned16(z_p) || !aligned16(m_p) || !aligned16(logs_p) || !aligned16(neg_cent_out) || !aligned16(workspace))
         return MAS_ERR_ALIGNMENT;
-    return cost_launch(z_p, m_p, logs_p, neg_cent_out, stats_out, workspace, workspace_bytes, B, D, T, S,
+    return cost_launch(z_p, m_p, logs_p, neg_cent_out, stats_out, nullptr, workspace, workspace_bytes, B, D, T, S,
                        static_cast<cudaStream_t>(stream));
 }
 
@@ -157,7 +158,10 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
     float *nc = neg_cent_out ? neg_cent_out : reinterpret_cast<float *>(ws + cost_ws + 256);
     unsigned char *dp_ws = ws + cost_ws + 256 + align_up((size_t)B * T * S * 4, 256);
     const size_t dp_ws_bytes = align_up(dp_workspace_bytes(B, T, S), 256);
-    rc = cost_launch(z_p, m_p, logs_p, nc, noise ? stats : nullptr, ws, cost_ws, B, D, T, S, st);
+    // mel tiles wholly past t_y are skipped only when the plane is private scratch: a caller who asked for
+    // neg_cent_out gets every cell the reference would compute
+    rc = cost_launch(z_p, m_p, logs_p, nc, noise ? stats : nullptr, neg_cent_out ? nullptr : t_ys, ws, cost_ws, B, D,
+                     T, S, st);
     if (rc) return rc;
     if (noise) {
         rc = add_noise_launch(nc, noise, stats, noise_scale, nc, (size_t)B * T * S, st);

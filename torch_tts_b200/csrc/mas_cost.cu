@@ -146,17 +146,36 @@ __global__ void mas_add_noise_kernel(const float *__restrict__ nc, const float *
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// mas_cost_tc.cu
+bool cost_tc_supported(int B, int D, int T, int S);
+size_t cost_tc_workspace_bytes(int B, int D, int T, int S);
+int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
+                   const int32_t *t_ys, void *workspace, size_t workspace_bytes, int B, int D, int T, int S,
+                   cudaStream_t stream);
+
+static bool use_tc(int B, int D, int T, int S)
+{
+    const char *e = getenv("MAS_COST_IMPL");  // "simt" forces the fp32 SIMT contraction (yardstick / A-B runs)
+    if (e && e[0] == 's') return false;
+    return cost_tc_supported(B, D, T, S);
+}
+
 size_t cost_workspace_bytes(int B, int D, int T, int S)
 {
-    (void)T;
     const size_t prior = align_up((size_t)B * D * S * 4, 256);
-    return 2 * prior + align_up((size_t)B * S * 4, 256);
+    const size_t simt = 2 * prior + align_up((size_t)B * S * 4, 256);
+    const size_t tc = cost_tc_supported(B, D, T, S) ? cost_tc_workspace_bytes(B, D, T, S) : 0;
+    return simt > tc ? simt : tc;
 }
 
 int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
-                void *workspace, size_t workspace_bytes, int B, int D, int T, int S, cudaStream_t stream)
+                const int32_t *t_ys, void *workspace, size_t workspace_bytes, int B, int D, int T, int S,
+                cudaStream_t stream)
 {
     if (workspace_bytes < cost_workspace_bytes(B, D, T, S) || !workspace) return MAS_ERR_WORKSPACE;
+    if (use_tc(B, D, T, S))
+        return cost_tc_launch(z_p, m_p, logs_p, neg_cent_out, stats_out, t_ys, workspace, workspace_bytes, B, D, T, S,
+                              stream);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     const size_t prior = align_up((size_t)B * D * S * 4, 256);
     float *r = reinterpret_cast<float *>(ws);
