@@ -33,6 +33,13 @@ int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *
                 cudaStream_t stream);
 int add_noise_launch(const float *nc, const float *noise, const double *stats, float scale, float *out, size_t n,
                      cudaStream_t stream);
+// mas_fused.cu
+bool fused_supported(int B, int D, int T, int S);
+size_t fused_flags_bytes(int B, int T);
+int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const int32_t *t_ys, const int32_t *t_xs,
+                 float *neg_cent, bool skip_dead_tiles, void *path_out, int path_dtype, int32_t *dur_out,
+                 int32_t *idx_out, int32_t *status_out, void *cost_ws, size_t cost_ws_bytes, void *dp_ws,
+                 size_t dp_ws_bytes, uint32_t *flags, int B, int D, int T, int S, cudaStream_t stream);
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -126,13 +133,13 @@ int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p, fl
                        static_cast<cudaStream_t>(stream));
 }
 
-// fused workspace layout: [cost ws][stats 256 B][neg_cent plane][dp ws]
+// fused workspace layout: [cost ws][stats 256 B][neg_cent plane][dp ws][tile flags]
 size_t mas_fused_align_workspace_bytes(int B, int D, int T, int S, int with_noise)
 {
     (void)with_noise;
     if (check_shape(B, T, S) != MAS_OK || D < 1) return 0;
     return align_up(cost_workspace_bytes(B, D, T, S), 256) + 256 + align_up((size_t)B * T * S * 4, 256) +
-           align_up(dp_workspace_bytes(B, T, S), 256);
+           align_up(dp_workspace_bytes(B, T, S), 256) + fused_flags_bytes(B, T);
 }
 
 int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p, const int32_t *t_ys,
@@ -158,6 +165,12 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
     float *nc = neg_cent_out ? neg_cent_out : reinterpret_cast<float *>(ws + cost_ws + 256);
     unsigned char *dp_ws = ws + cost_ws + 256 + align_up((size_t)B * T * S * 4, 256);
     const size_t dp_ws_bytes = align_up(dp_workspace_bytes(B, T, S), 256);
+    if (!noise && fused_supported(B, D, T, S)) {
+        // one kernel: contraction CTAs publish cost tiles, DP CTAs consume them (mas_fused.cu)
+        uint32_t *flags = reinterpret_cast<uint32_t *>(dp_ws + dp_ws_bytes);
+        return fused_launch(z_p, m_p, logs_p, t_ys, t_xs, nc, neg_cent_out == nullptr, path_out, path_dtype, dur_out,
+                            idx_out, status_out, ws, cost_ws, dp_ws, dp_ws_bytes, flags, B, D, T, S, st);
+    }
     // mel tiles wholly past t_y are skipped only when the plane is private scratch: a caller who asked for
     // neg_cent_out gets every cell the reference would compute
     rc = cost_launch(z_p, m_p, logs_p, nc, noise ? stats : nullptr, neg_cent_out ? nullptr : t_ys, ws, cost_ws, B, D,

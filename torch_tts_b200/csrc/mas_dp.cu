@@ -1,68 +1,13 @@
-// mas_dp.cu -- monotonic alignment search (forward DP + backtrack) for sm_100a.
-//
-// Replaces maximum_path_each / maximum_path_c of the reference
-// (vits2/monotonic_align/core.pyx:7-42) and the zero-init / dtype cast of its
-// Python wrapper (vits2/monotonic_align/__init__.py:14,19).  Bit-exact: per
-// cell one fp32 compare-select and one fp32 add, in the reference's operand
-// order; no FMA, no reassociation.
-//
-// Mapping (one CTA per utterance, 4 DP warps + 1 producer warp):
-//   * text columns are blocked over the 128 DP threads, C = ceil(S/128)
-//     consecutive columns per thread; the running DP row lives in registers.
-//   * the left neighbour crosses lanes with one __shfl_up per row and crosses
-//     warps through a small shared-memory ring; warp w runs one chunk of R mel
-//     rows behind warp w-1 (wavefront), one __syncthreads per chunk step.
-//   * the producer warp streams the cost plane through an 8-stage ring of
-//     shared-memory tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier)
-//     and zero-fills the dense path output while the DP runs.
-//   * 1 bit per cell (ballot of "took the diagonal") is kept on chip so the
-//     backtrack never re-reads the cost; every 32 rows the column each cell
-//     backtracks to ("hop") is checkpointed, so the backtrack is T/32 dependent
-//     hops followed by T/32 independent 32-row walks, one per thread.
-//   * long utterances whose bits/hops exceed shared memory spill them to the
-//     caller's workspace (L2-resident).
-#include "mas_common.cuh"
+// mas_dp.cu -- standalone launch of the MAS forward DP + backtrack (role code in mas_dp.cuh),
+// the shared-memory plan, and the small helper kernels (lengths from mask, launch order, expand).
+#include "mas_dp.cuh"
 
 namespace mas {
-
-constexpr int kDpWarps = 4;
-constexpr int kDpThreads = kDpWarps * 32;
-constexpr int kThreads = kDpThreads + 32;  // + producer warp
-constexpr int kStages = 8;
-constexpr int kCheck = 32;  // checkpoint interval (rows)
-constexpr int kSmemBudget = 227 * 1024;
-constexpr int kZeroBytes = 8192;  // zeroed shared buffer the path zero-fill bulk-stores from
-
-struct DpParams {
-    const float *neg_cent;
-    const int32_t *t_ys;
-    const int32_t *t_xs;
-    const int32_t *order;  // nullable: CTA -> utterance (longest first)
-    unsigned char *path;
-    int32_t *dur;
-    int32_t *idx;
-    int32_t *status;
-    uint32_t *bits_ws;      // global spill (per CTA region), used when !bits_in_smem
-    unsigned char *hop_ws;  // global spill (per CTA region), used when !hop_in_smem
-    int B, T, S;
-    int R;  // mel rows per chunk: 4, 8, 16 or 32
-    int path_dtype;
-    int bits_in_smem, hop_in_smem;
-    uint32_t off_bits, off_hop, off_stage, stage_bytes, off_bnd_v, off_bnd_o, off_idx, off_end, off_entry, off_bar, off_zero;
-    unsigned long long bits_words_per_cta, hop_bytes_per_cta;
-};
-
-struct DpPlan {
-    DpParams p;
-    int C;
-    size_t smem_bytes;
-    size_t ws_bits_bytes, ws_hop_bytes;
-};
 
 // ---------------------------------------------------------------------------
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
-static bool plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, bool hop_smem)
+bool dp_plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, bool hop_smem)
 {
     const int S_pad = kDpThreads * C;
     const int WPR = kDpWarps * C;
@@ -92,6 +37,8 @@ static bool plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, boo
     off += (size_t)S_pad * 4;
     p.off_entry = (uint32_t)off;
     off += align_up((size_t)hop_rows * 2, 16);
+    p.off_misc = (uint32_t)off;
+    off += 16;
     p.bits_in_smem = bits_smem;
     p.hop_in_smem = hop_smem;
     p.bits_words_per_cta = (unsigned long long)T * WPR;
@@ -102,7 +49,7 @@ static bool plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, boo
 }
 
 // rows_hint > 0 forces the chunk height (tuning knob, MAS_DP_ROWS).
-static bool make_plan(DpPlan &pl, int B, int T, int S, int rows_hint)
+bool dp_make_plan(DpPlan &pl, int B, int T, int S, int rows_hint)
 {
     const int C = (S + kDpThreads - 1) / kDpThreads;
     if (C < 1 || C > 8) return false;
@@ -112,7 +59,7 @@ static bool make_plan(DpPlan &pl, int B, int T, int S, int rows_hint)
         const bool bits_smem = (mode == 0), hop_smem = (mode <= 1);
         for (int i = 0; i < 3 && !ok; ++i) {
             int R = rows_hint > 0 ? rows_hint : rs_all[i];
-            ok = plan_try(pl, T, S, C, R, bits_smem, hop_smem);
+            ok = dp_plan_try(pl, T, S, C, R, bits_smem, hop_smem);
             if (rows_hint > 0) break;
         }
     }
@@ -122,441 +69,14 @@ static bool make_plan(DpPlan &pl, int B, int T, int S, int rows_hint)
     return true;
 }
 
-// ---------------------------------------------------------------------------
-// device
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void zero_bytes_warp(unsigned char *ptr, size_t bytes, int lane)
-{
-    // generic zero fill by one warp: 2-byte head/tail, 16-byte body
-    size_t head = (16 - (reinterpret_cast<uintptr_t>(ptr) & 15)) & 15;
-    if (head > bytes) head = bytes;
-    for (size_t i = lane * 2; i < head; i += 64) *reinterpret_cast<uint16_t *>(ptr + i) = 0;
-    size_t body = (bytes - head) & ~(size_t)15;
-    for (size_t i = (size_t)lane * 16; i < body; i += 512) st_global_v4_zero(ptr + head + i);
-    for (size_t i = head + body + lane * 2; i < bytes; i += 64) *reinterpret_cast<uint16_t *>(ptr + i) = 0;
-}
-
-__device__ __forceinline__ void store_one(unsigned char *path_b, size_t cell, int path_dtype)
-{
-    if (path_dtype == MAS_PATH_F32)
-        reinterpret_cast<float *>(path_b)[cell] = 1.0f;
-    else if (path_dtype == MAS_PATH_I32)
-        reinterpret_cast<int32_t *>(path_b)[cell] = 1;
-    else
-        reinterpret_cast<uint16_t *>(path_b)[cell] = (uint16_t)path_one_bits(path_dtype);
-}
-
-// NR mel rows (4 in the main loop, 1 for the tail) of the forward DP for this
-// thread's C consecutive columns.
-//   v/org   running DP row and checkpoint origin per column (registers)
-//   trow    &tile[r * S + x0]: this thread's first cost of the first row
-//   carry   value/origin of column x0-1 after the previous row (lane 0 only matters)
-//   bin_*   boundary ring written by the warp to the left, slot of row y
-//   bout_*  this warp's boundary ring, slot of row y (lane 31 writes)
-//   brow    direction words of row y for this warp (lane 0 writes)
-//   kExact  false: max via FMNMX (short dependency chain); exact while every cost is
-//           finite, which `fin` tracks (it turns NaN as soon as one is not).
-//           true: the reference's compare-select, bit-for-bit also for NaN/Inf input.
-template <int C, int NR, bool kEdge, bool kVec, bool kExact>
-__device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float (&fin)[C], const float *trow, int S,
-                                        float &carry_v, int &carry_o, const float *bin_v, const int *bin_o,
-                                        float *bout_v, int *bout_o, uint32_t *brow, int y, int x0, int lane)
-{
-    constexpr int WPR = kDpWarps * C;
-    float cost[NR][C];
-    float lv[NR + 1];
-    int lo[NR + 1];
-    lv[0] = carry_v;
-    lo[0] = carry_o;
-    // ---- all loads for the NR rows up front
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        const float *src = trow + (size_t)i * S;
-        if (kVec && (C % 4 == 0)) {
-#pragma unroll
-            for (int k = 0; k < C; k += 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(src + k);
-                cost[i][k] = t.x, cost[i][k + 1] = t.y, cost[i][k + 2] = t.z, cost[i][k + 3] = t.w;
-            }
-        } else if (kVec && (C % 2 == 0)) {
-#pragma unroll
-            for (int k = 0; k < C; k += 2) {
-                const float2 t = *reinterpret_cast<const float2 *>(src + k);
-                cost[i][k] = t.x, cost[i][k + 1] = t.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; ++k) cost[i][k] = src[k];
-        }
-    }
-    if (NR == 4) {
-        const float4 t = *reinterpret_cast<const float4 *>(bin_v);
-        const int4 u = *reinterpret_cast<const int4 *>(bin_o);
-        lv[1] = t.x, lv[2] = t.y, lv[3] = t.z, lv[4] = t.w;
-        lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            lv[i + 1] = bin_v[i];
-            lo[i + 1] = bin_o[i];
-        }
-    }
-    float ov[NR];
-    int oo[NR];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        float up_v = __shfl_up_sync(kFullMask, v[C - 1], 1);
-        int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
-        if (lane == 0) {
-            up_v = lv[i];
-            up_o = lo[i];
-        }
-        uint32_t words[C];
-#pragma unroll
-        for (int k = C - 1; k >= 0; --k) {
-            const float v_prev = (k == 0) ? up_v : v[k - 1];  // value[y-1, x-1]  (core.pyx:21-27)
-            const int o_prev = (k == 0) ? up_o : org[k - 1];
-            const float v_cur = v[k];                          // value[y-1, x]    (core.pyx:17-20)
-            // Cython's max(v_prev, v_cur) is (v_cur > v_prev) ? v_cur : v_prev; with no NaN in
-            // flight that is fmaxf (one FMNMX instead of FSETP -> FSEL on the dependency chain)
-            float m;
-            if (kExact) {
-                m = (v_cur > v_prev) ? v_cur : v_prev;
-            } else {
-                m = fmaxf(v_prev, v_cur);
-                fin[k] = fmaf(cost[i][k], 0.0f, fin[k]);  // NaN iff some cost was NaN or +-Inf
-            }
-            // backtrack rule, core.pyx:32: index == y or value[y-1,x] < value[y-1,x-1]
-            // (the "index != 0" guard is applied by the backtrack itself)
-            bool diag = v_cur < v_prev;
-            if (kEdge) diag = diag || (x0 + k == y + i);
-            float nv = cost[i][k] + m;  // core.pyx:28
-            int no = diag ? o_prev : org[k];
-            if (kEdge) {
-                const bool in_band = (x0 + k <= y + i);  // upper band edge, core.pyx:16
-                nv = in_band ? nv : v_cur;
-                no = in_band ? no : org[k];
-            }
-            v[k] = nv;
-            org[k] = no;
-            words[k] = __ballot_sync(kFullMask, diag);
-        }
-        ov[i] = v[C - 1];
-        oo[i] = org[C - 1];
-        if (lane == 0) {
-            uint32_t *dst = brow + (size_t)i * WPR;
-            if (C == 2) {
-                *reinterpret_cast<uint2 *>(dst) = make_uint2(words[0], words[1]);
-            } else if (C == 4) {
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < C; ++k) dst[k] = words[k];
-            }
-        }
-    }
-    if (lane == 31) {
-        if (NR == 4) {
-            *reinterpret_cast<float4 *>(bout_v) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-            *reinterpret_cast<int4 *>(bout_o) = make_int4(oo[0], oo[1], oo[2], oo[3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                bout_v[i] = ov[i];
-                bout_o[i] = oo[i];
-            }
-        }
-    }
-    carry_v = lv[NR];
-    carry_o = lo[NR];
-}
-
-template <int C, bool kEdge, bool kVec, bool kExact>
-__device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float (&fin)[C], const float *tile, int S,
-                                         int rows, int row0,
-                                         int ring_mask, float &carry_v, int &carry_o, const float *bin_v,
-                                         const int *bin_o, float *bout_v, int *bout_o, uint32_t *bits_w, int x0,
-                                         int lane)
-{
-    constexpr int WPR = kDpWarps * C;
-    // Threads whose columns lie past S re-read the last real columns instead of whatever
-    // follows the row: their results are never used, but they must not invent NaNs.
-    // (A thread straddling S reads at most C-1 floats of the next row, or of the zeroed
-    // pad the producer keeps behind every tile.)
-    const float *trow = tile + (x0 < S ? x0 : S - C);
-    uint32_t *brow = bits_w + (size_t)row0 * WPR;
-    int r = 0;
-    for (; r + 4 <= rows; r += 4) {
-        const int slot = (row0 + r) & ring_mask;
-        dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
-                                   bout_o + slot, brow, row0 + r, x0, lane);
-        trow += (size_t)4 * S;
-        brow += 4 * WPR;
-    }
-    for (; r < rows; ++r) {
-        const int slot = (row0 + r) & ring_mask;
-        dp_rows<C, 1, kEdge, kVec, kExact>(v, org, fin, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
-                                   bout_o + slot, brow, row0 + r, x0, lane);
-        trow += S;
-        brow += WPR;
-    }
-}
-
-// checkpoint row c_j: c_0 = 0, c_j = 32 j - 1
-__device__ __forceinline__ int check_row(int j) { return j == 0 ? 0 : kCheck * j - 1; }
-
 template <int C, bool kVec>
 __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int lane = tid & 31;
     const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
-    const int T = p.T, S = p.S, R = p.R;
-    const int t_y = p.t_ys[b], t_x = p.t_xs[b];
-    constexpr int S_pad = kDpThreads * C;
-    constexpr int WPR = kDpWarps * C;
-    const int esize = path_elem_size(p.path_dtype);
-    const size_t plane = (size_t)T * S;
-    unsigned char *path_b = p.path + (size_t)b * plane * esize;
-
-    // ---- length contract (anything else is UB in the reference) ----
-    if (!(t_x >= 1 && t_x <= t_y && t_y <= T && t_x <= S)) {
-        {
-            const size_t total = plane * esize;
-            const size_t seg = align_up((total + kThreads / 32 - 1) / (kThreads / 32), 512);
-            size_t lo = (size_t)warp * seg, hi = lo + seg;
-            if (lo > total) lo = total;
-            if (hi > total) hi = total;
-            if (hi > lo) zero_bytes_warp(path_b + lo, hi - lo, lane);
-        }
-        if (p.dur)
-            for (int x = tid; x < S; x += kThreads) p.dur[(size_t)b * S + x] = 0;
-        if (p.idx)
-            for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = -1;
-        if (p.status && tid == 0) p.status[b] = MAS_UTT_BAD_LENGTHS;
-        return;
-    }
-
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
-    uint32_t *bits = p.bits_in_smem ? reinterpret_cast<uint32_t *>(smem + p.off_bits)
-                                    : p.bits_ws + (size_t)blockIdx.x * p.bits_words_per_cta;
-    unsigned char *hop = p.hop_in_smem ? (smem + p.off_hop) : p.hop_ws + (size_t)blockIdx.x * p.hop_bytes_per_cta;
-    float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);  // [kDpWarps + 1][2R]
-    int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
-    uint16_t *idx_s = reinterpret_cast<uint16_t *>(smem + p.off_idx);
-    int *end_s = reinterpret_cast<int *>(smem + p.off_end);
-    uint16_t *entry_s = reinterpret_cast<uint16_t *>(smem + p.off_entry);
-    unsigned char *zero_s = smem + p.off_zero;
-
-    const int ring = 2 * R;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
-        fence_mbar_init();
-    }
-    // ring 0 stands in for "the warp left of warp 0": column -1 is the -1e9 sentinel (core.pyx:24)
-    for (int i = tid; i < ring; i += kThreads) {
-        bnd_v[i] = kNeg;
-        bnd_o[i] = 0;
-    }
-    for (int i = tid; i < kZeroBytes / 16; i += kThreads) reinterpret_cast<uint4 *>(zero_s)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async();  // zero_s is read by the bulk-store engine
-    __syncthreads();
-
-    const int n_chunks = (t_y + R - 1) / R;
-    const int n_steps = n_chunks + kDpWarps - 1;
-    const int ring_mask = ring - 1;
-    const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
-    const size_t total_bytes = (size_t)p.B * plane * 4;
-
-    // Pass 0 runs the short-chain body; only if it met a non-finite cost does pass 1 redo the
-    // forward DP with the reference's exact compare-select (NaN/Inf semantics of core.pyx).
-    for (int pass = 0; pass < 2; ++pass) {
-        const int g0 = pass * n_chunks;  // running tile number: stage = g % kStages, parity = (g / kStages) & 1
-        bool saw_nonfinite = false;
-        if (warp == kDpWarps) {
-            // =================== producer warp ===================
-            auto issue_tile = [&](int c) {
-                const int g = g0 + c;
-                const int row0 = c * R;
-                const int rows = min(R, t_y - row0);
-                const size_t start = (utt_elem0 + (size_t)row0 * S) * 4;
-                const uint32_t mis = (uint32_t)(start & 15);
-                const size_t src0 = start - mis;
-                const uint32_t want = mis + (uint32_t)rows * S * 4;
-                uint32_t bulk = (want + 15u) & ~15u;
-                unsigned char *dst = smem + p.off_stage + (size_t)(g % kStages) * p.stage_bytes;
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(p.neg_cent) + src0;
-                // finite pad behind the tile for the one thread whose columns straddle S
-                *reinterpret_cast<uint4 *>(dst + ((want + 15u) & ~15u)) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4 *>(dst + ((want + 15u) & ~15u) + 16) = make_uint4(0, 0, 0, 0);
-                if (src0 + bulk > total_bytes) {
-                    // the 16-byte round-up would run past the tensor: finish the tail by hand
-                    bulk = want & ~15u;
-                    for (uint32_t o = bulk; o < ((want + 15u) & ~15u); o += 4)
-                        *reinterpret_cast<float *>(dst + o) =
-                            (o < want) ? *reinterpret_cast<const float *>(src + o) : 0.0f;
-                }
-                mbar_arrive_expect_tx(&full[g % kStages], bulk);
-                if (bulk) bulk_g2s(dst, src, bulk, &full[g % kStages]);
-            };
-            if (lane == 0) {
-                const int pre = min(kStages, n_chunks);
-                for (int c = 0; c < pre; ++c) issue_tile(c);
-            }
-            // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
-            // zeroed shared buffer when the plane is 16-byte aligned, plain stores otherwise
-            const size_t pbytes = (pass == 0) ? plane * esize : 0;
-            const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
-            const size_t quota = align_up((pbytes + n_steps - 1) / n_steps, 512);
-            for (int step = 0; step < n_steps; ++step) {
-                size_t lo = (size_t)step * quota, hi = lo + quota;
-                if (lo > pbytes) lo = pbytes;
-                if (hi > pbytes || step == n_steps - 1) hi = pbytes;
-                if (hi > lo) {
-                    if (bulk_ok) {
-                        if (lane == 0) {
-                            for (size_t o = lo; o < hi; o += kZeroBytes)
-                                bulk_s2g(path_b + o, zero_s, (uint32_t)min((size_t)kZeroBytes, hi - o));
-                            bulk_commit();
-                        }
-                    } else {
-                        zero_bytes_warp(path_b + lo, hi - lo, lane);
-                    }
-                }
-                __syncthreads();
-                const int freed = step - (kDpWarps - 1);
-                if (lane == 0 && freed >= 0 && freed + kStages < n_chunks) issue_tile(freed + kStages);
-            }
-            if (pass == 0 && bulk_ok && lane == 0) bulk_wait_all();  // zeros land before the ones are scattered
-        } else {
-            // =================== DP warps ===================
-            const int w = warp;
-            const int x0 = (w * 32 + lane) * C;
-            float v[C], fin[C];
-            int org[C];
-#pragma unroll
-            for (int k = 0; k < C; ++k) {
-                v[k] = kNeg;
-                org[k] = x0 + k;
-                fin[k] = 0.0f;
-            }
-            // value left of column x0 for the first row: 0 for column 0 at y == 0 (core.pyx:22-23)
-            float carry_v = (w == 0) ? 0.0f : kNeg;
-            int carry_o = 0;
-            const float *bin_v = bnd_v + (size_t)w * ring;
-            const int *bin_o = bnd_o + (size_t)w * ring;
-            float *bout_v = bnd_v + (size_t)(w + 1) * ring;
-            int *bout_o = bnd_o + (size_t)(w + 1) * ring;
-            uint32_t *bits_w = bits + w * C;
-            const int edge_rows = (w + 1) * 32 * C;  // rows where a column of this warp is still above the diagonal
-            for (int step = 0; step < n_steps; ++step) {
-                const int c = step - w;
-                if (c >= 0 && c < n_chunks) {
-                    const int g = g0 + c;
-                    const int row0 = c * R;
-                    const int rows = min(R, t_y - row0);
-                    const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
-                    const float *tile = reinterpret_cast<const float *>(smem + p.off_stage +
-                                                                        (size_t)(g % kStages) * p.stage_bytes + mis);
-                    mbar_wait(&full[g % kStages], (uint32_t)(g / kStages) & 1u);
-                    const bool edge = row0 < edge_rows;
-#define MAS_CHUNK(EDGE, EXACT)                                                                                    \
-    dp_chunk<C, EDGE, kVec, EXACT>(v, org, fin, tile, S, rows, row0, ring_mask, carry_v, carry_o, bin_v, bin_o, \
-                                   bout_v, bout_o, bits_w, x0, lane)
-                    if (pass == 0) {
-                        if (edge)
-                            MAS_CHUNK(true, false);
-                        else
-                            MAS_CHUNK(false, false);
-                    } else {
-                        if (edge)
-                            MAS_CHUNK(true, true);
-                        else
-                            MAS_CHUNK(false, true);
-                    }
-#undef MAS_CHUNK
-                    // checkpoint after rows 31, 63, ...: remember where each column backtracks to, restart origins
-                    if (((row0 + rows) & (kCheck - 1)) == 0) {
-                        unsigned char *hrow = hop + (size_t)((row0 + rows) / kCheck) * S_pad;
-#pragma unroll
-                        for (int k = 0; k < C; ++k) {
-                            hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
-                            org[k] = x0 + k;
-                        }
-                        // the right-hand warp must see the restarted origin of our last column
-                        if (lane == 31) bout_o[(row0 + rows - 1) & ring_mask] = x0 + C - 1;
-                    }
-                }
-                __syncthreads();
-            }
-            // origin of the last row relative to its checkpoint -> hop row 0
-#pragma unroll
-            for (int k = 0; k < C; ++k) {
-                hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
-                saw_nonfinite = saw_nonfinite || (fin[k] != fin[k]);
-            }
-        }
-        if (pass == 1 || !__syncthreads_or(saw_nonfinite)) break;
-    }
-    if (!p.bits_in_smem || !p.hop_in_smem) __threadfence_block();
-    __syncthreads();
-
-    // =================== backtrack ===================
-    const int y_last = t_y - 1;
-    const int J = t_y / kCheck;  // checkpoints stored: after rows 31, 63, ..., 32 J - 1
-    if (tid == 0) {
-        // level 1: one dependent load per 32 rows
-        int c = t_x - 1;
-        c -= hop[c];  // column at row c_J
-        entry_s[J] = (uint16_t)c;
-        for (int j = J; j >= 1; --j) {
-            c -= hop[(size_t)j * S_pad + c];  // column at row c_{j-1}
-            entry_s[j - 1] = (uint16_t)c;
-        }
-        idx_s[0] = 0;
-    }
-    __syncthreads();
-    // level 2: independent walks of <= 32 rows, one per thread
-    for (int j = tid; j <= J; j += kThreads) {
-        const int y_lo = check_row(j) + 1;
-        int y_top, cur;
-        if (j < J) {
-            y_top = check_row(j + 1);
-            cur = entry_s[j + 1];
-        } else {
-            y_top = y_last;
-            cur = t_x - 1;
-        }
-        for (int y = y_top; y >= y_lo; --y) {
-            idx_s[y] = (uint16_t)cur;
-            const int q = cur / C;
-            const uint32_t wd = bits[(size_t)y * WPR + (q >> 5) * C + (cur - q * C)];
-            cur -= (cur != 0) ? (int)((wd >> (q & 31)) & 1u) : 0;  // core.pyx:32 "index != 0 and ..."
-        }
-    }
-    for (int x = tid; x < S_pad; x += kThreads) end_s[x] = -1;
-    __syncthreads();
-
-    // =================== outputs ===================
-    for (int y = tid; y < t_y; y += kThreads) {
-        const int c = idx_s[y];
-        store_one(path_b, (size_t)y * S + c, p.path_dtype);
-        if (y == y_last || idx_s[y + 1] != c) end_s[c] = y;
-    }
-    if (p.idx) {
-        for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = (y < t_y) ? (int)idx_s[y] : -1;
-    }
-    if (p.status && tid == 0) p.status[b] = MAS_UTT_OK;
-    if (p.dur) {
-        __syncthreads();
-        for (int x = tid; x < S; x += kThreads) {
-            int d = 0;
-            if (x < t_x) d = end_s[x] - (x > 0 ? end_s[x - 1] : -1);
-            p.dur[(size_t)b * S + x] = d;
-        }
-    }
+    uint32_t g_base = 0;
+    dp_role_init(p, smem);
+    dp_role<C, kVec>(p, smem, b, blockIdx.x, g_base);
 }
 
 // ---------------------------------------------------------------------------
@@ -633,7 +153,7 @@ static int env_int(const char *name, int dflt)
 size_t dp_workspace_bytes(int B, int T, int S)
 {
     DpPlan pl{};
-    if (!make_plan(pl, B, T, S, env_int("MAS_DP_ROWS", 0))) return 0;
+    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_ROWS", 0))) return 0;
     return align_up((size_t)B * 4, 256) + align_up(pl.ws_bits_bytes, 256) + align_up(pl.ws_hop_bytes, 256);
 }
 
@@ -662,12 +182,14 @@ static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
     return vec ? launch_dp_cv<C, true>(pl, stream) : launch_dp_cv<C, false>(pl, stream);
 }
 
-int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
-              int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace, size_t workspace_bytes, int B,
-              int T, int S, cudaStream_t stream)
+// fills pl (shared-memory plan + parameters) without launching; `order_out` receives the workspace slot
+// of the launch-order array
+int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
+               int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
+               size_t workspace_bytes, int B, int T, int S, int32_t **order_out)
 {
-    DpPlan pl{};
-    if (!make_plan(pl, B, T, S, env_int("MAS_DP_ROWS", 0))) return MAS_ERR_UNSUPPORTED_SHAPE;
+    pl = DpPlan{};
+    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_ROWS", 0))) return MAS_ERR_UNSUPPORTED_SHAPE;
     const size_t need = dp_workspace_bytes(B, T, S);
     if (need && (!workspace || workspace_bytes < need)) return MAS_ERR_WORKSPACE;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -679,15 +201,31 @@ int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, v
     p.dur = dur_out;
     p.idx = idx_out;
     p.status = status_out;
+    p.flags = nullptr;
+    p.flag_tiles = 0;
+    p.order = nullptr;
     p.B = B;
     p.T = T;
     p.S = S;
     p.path_dtype = path_dtype;
-    int32_t *order = reinterpret_cast<int32_t *>(ws);
+    if (order_out) *order_out = reinterpret_cast<int32_t *>(ws);
     ws += align_up((size_t)B * 4, 256);
     p.bits_ws = reinterpret_cast<uint32_t *>(ws);
     ws += align_up(pl.ws_bits_bytes, 256);
     p.hop_ws = ws;
+    return MAS_OK;
+}
+
+int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
+              int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace, size_t workspace_bytes, int B,
+              int T, int S, cudaStream_t stream)
+{
+    DpPlan pl;
+    int32_t *order = nullptr;
+    int rc = dp_prepare(pl, neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, workspace,
+                        workspace_bytes, B, T, S, &order);
+    if (rc) return rc;
+    DpParams &p = pl.p;
     // Length bucketing: when the batch is more than one wave of CTAs, launch the
     // longest utterances first so short ones fill in behind them.
     int dev = 0, sms = 148;
