@@ -159,7 +159,11 @@ int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, floa
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = B * plan.p.m_tiles;
-    const int grid = n_tiles < sms ? n_tiles : sms;
+    int grid = n_tiles < sms ? n_tiles : sms;
+    {
+        const char *g = getenv("MAS_TC_GRID");  // experiments: restrict the contraction to fewer SMs
+        if (g && *g && atoi(g) > 0 && atoi(g) < grid) grid = atoi(g);
+    }
     if (stats_out)
         mas_cost_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
     else

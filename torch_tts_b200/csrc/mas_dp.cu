@@ -7,24 +7,26 @@ namespace mas {
 // ---------------------------------------------------------------------------
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
-bool dp_plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, bool hop_smem)
+bool dp_plan_try(DpPlan &pl, int T, int S, int C, int stages, bool bits_smem, bool hop_smem)
 {
+    const int R = dp_chunk_rows(C);
     const int S_pad = kDpThreads * C;
-    const int WPR = kDpWarps * C;
+    const int n_blk = (T + kCheck - 1) / kCheck;  // 32-row blocks of decision words
     const int hop_rows = T / kCheck + 2;
     size_t off = 0;
     DpParams &p = pl.p;
     p.R = R;
+    p.stages = stages;
     p.off_bar = (uint32_t)off;
     off += 128;
     p.off_bits = (uint32_t)off;
-    if (bits_smem) off += align_up((size_t)T * WPR * 4, 16);
+    if (bits_smem) off += align_up((size_t)n_blk * S_pad * 4, 16);
     p.off_hop = (uint32_t)off;
     if (hop_smem) off += align_up((size_t)hop_rows * S_pad, 16);
     p.stage_bytes = (uint32_t)align_up((size_t)R * S * 4 + 16 + 64, 128);  // tile + misalignment + zeroed pad
     off = align_up(off, 128);
     p.off_stage = (uint32_t)off;
-    off += (size_t)kStages * p.stage_bytes;
+    off += (size_t)stages * p.stage_bytes;
     p.off_bnd_v = (uint32_t)off;
     off += (size_t)(kDpWarps + 1) * 2 * R * 4;
     p.off_bnd_o = (uint32_t)off;
@@ -32,7 +34,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, bool ho
     p.off_zero = (uint32_t)off;
     off += kZeroBytes;
     p.off_idx = (uint32_t)off;
-    off += align_up((size_t)T * 2, 16);
+    off += align_up((size_t)T * 2 + 2, 16);
     p.off_end = (uint32_t)off;
     off += (size_t)S_pad * 4;
     p.off_entry = (uint32_t)off;
@@ -41,26 +43,26 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int C, int R, bool bits_smem, bool ho
     off += 16;
     p.bits_in_smem = bits_smem;
     p.hop_in_smem = hop_smem;
-    p.bits_words_per_cta = (unsigned long long)T * WPR;
+    p.bits_words_per_cta = (unsigned long long)n_blk * S_pad;
     p.hop_bytes_per_cta = (unsigned long long)align_up((size_t)hop_rows * S_pad, 16);
     pl.smem_bytes = off;
     pl.C = C;
     return off <= (size_t)kSmemBudget;
 }
 
-// rows_hint > 0 forces the chunk height (tuning knob, MAS_DP_ROWS).
-bool dp_make_plan(DpPlan &pl, int B, int T, int S, int rows_hint)
+// Deepest cost-tile ring that fits next to on-chip decision bits / hops; long utterances spill the
+// bits (then the hops) to the workspace.  stages_hint > 0 forces the ring depth (MAS_DP_STAGES).
+bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint)
 {
     const int C = (S + kDpThreads - 1) / kDpThreads;
     if (C < 1 || C > 8) return false;
-    const int rs_all[4] = {16, 8, 4, 32};
     bool ok = false;
     for (int mode = 0; mode < 3 && !ok; ++mode) {
         const bool bits_smem = (mode == 0), hop_smem = (mode <= 1);
-        for (int i = 0; i < 3 && !ok; ++i) {
-            int R = rows_hint > 0 ? rows_hint : rs_all[i];
-            ok = dp_plan_try(pl, T, S, C, R, bits_smem, hop_smem);
-            if (rows_hint > 0) break;
+        const int min_stages = (mode == 2) ? 2 : 3;
+        for (int st = (stages_hint > 0 ? stages_hint : 6); st >= min_stages && !ok; --st) {
+            ok = dp_plan_try(pl, T, S, C, st, bits_smem, hop_smem);
+            if (stages_hint > 0) break;
         }
     }
     if (!ok) return false;
@@ -153,7 +155,7 @@ static int env_int(const char *name, int dflt)
 size_t dp_workspace_bytes(int B, int T, int S)
 {
     DpPlan pl{};
-    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_ROWS", 0))) return 0;
+    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0))) return 0;
     return align_up((size_t)B * 4, 256) + align_up(pl.ws_bits_bytes, 256) + align_up(pl.ws_hop_bytes, 256);
 }
 
@@ -189,7 +191,7 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
                size_t workspace_bytes, int B, int T, int S, int32_t **order_out)
 {
     pl = DpPlan{};
-    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_ROWS", 0))) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0))) return MAS_ERR_UNSUPPORTED_SHAPE;
     const size_t need = dp_workspace_bytes(B, T, S);
     if (need && (!workspace || workspace_bytes < need)) return MAS_ERR_WORKSPACE;
     unsigned char *ws = static_cast<unsigned char *>(workspace);

@@ -12,14 +12,17 @@
 //     consecutive columns per thread; the running DP row lives in registers.
 //   * the left neighbour crosses lanes with one __shfl_up per row and crosses
 //     warps through a small shared-memory ring; warp w runs one chunk of R mel
-//     rows behind warp w-1 (wavefront), one __syncthreads per chunk step.
-//   * the producer warp streams the cost plane through an 8-stage ring of
-//     shared-memory tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier)
-//     and zero-fills the dense path output while the DP runs.
-//   * 1 bit per cell (ballot of "took the diagonal") is kept on chip so the
-//     backtrack never re-reads the cost; every 32 rows the column each cell
-//     backtracks to ("hop") is checkpointed, so the backtrack is T/32 dependent
-//     hops followed by T/32 independent 32-row walks, one per thread.
+//     rows behind warp w-1 (wavefront), one named barrier per chunk step.  Only every
+//     C-th link of the dependency chain crosses a lane, so a row costs about
+//     (shuffle + C * (max + add)) / C cycles of latency.
+//   * the producer warp streams the cost plane through a ring of shared-memory
+//     tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier) and zero-fills
+//     the dense path output with TMA bulk stores while the DP runs.
+//   * 1 bit per cell ("took the diagonal") is packed by each thread into one
+//     32-bit word per column per 32 rows (a predicated OR with an immediate) and
+//     kept on chip so the backtrack never re-reads the cost; every 32 rows the
+//     column each cell backtracks to ("hop") is checkpointed, so the backtrack is
+//     T/32 dependent hops followed by T/32 independent 32-row walks, one per thread.
 //   * long utterances whose bits/hops exceed shared memory spill them to the
 //     caller's workspace (L2-resident).
 #pragma once
@@ -31,11 +34,14 @@ namespace mas {
 constexpr int kDpWarps = 4;
 constexpr int kDpThreads = kDpWarps * 32;
 constexpr int kThreads = kDpThreads + 32;  // + producer warp
-constexpr int kStages = 8;
+constexpr int kMaxStages = 8;
 constexpr int kCheck = 32;  // checkpoint interval (rows)
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kDpBar = 3;     // named barrier of the DP role (kThreads threads)
 constexpr int kZeroBytes = 8192;  // zeroed shared buffer the path zero-fill bulk-stores from
+
+// mel rows per chunk (= per TMA tile) for C columns per thread: a stage stays <= 32 KB
+__host__ __device__ constexpr int dp_chunk_rows(int C) { return C <= 2 ? 32 : (C <= 4 ? 16 : 8); }
 
 struct DpParams {
     const float *neg_cent;
@@ -51,7 +57,8 @@ struct DpParams {
     uint32_t *bits_ws;      // global spill (per CTA region), used when !bits_in_smem
     unsigned char *hop_ws;  // global spill (per CTA region), used when !hop_in_smem
     int B, T, S;
-    int R;  // mel rows per chunk: 4, 8, 16 or 32
+    int R;       // mel rows per chunk = dp_chunk_rows(C)
+    int stages;  // cost-tile ring depth (2..kMaxStages)
     int path_dtype;
     int bits_in_smem, hop_in_smem;
     uint32_t off_bits, off_hop, off_stage, stage_bytes, off_bnd_v, off_bnd_o, off_idx, off_end, off_entry, off_bar, off_zero, off_misc;
@@ -92,20 +99,21 @@ __device__ __forceinline__ void store_one(unsigned char *path_b, size_t cell, in
 // NR mel rows (4 in the main loop, 1 for the tail) of the forward DP for this
 // thread's C consecutive columns.
 //   v/org   running DP row and checkpoint origin per column (registers)
+//   fin     turns NaN/Inf as soon as one cost was not finite (fast path only)
+//   wl      decision bits of this chunk, bit (bit0 + i) = row i of this call
 //   trow    &tile[r * S + x0]: this thread's first cost of the first row
 //   carry   value/origin of column x0-1 after the previous row (lane 0 only matters)
 //   bin_*   boundary ring written by the warp to the left, slot of row y
 //   bout_*  this warp's boundary ring, slot of row y (lane 31 writes)
-//   brow    direction words of row y for this warp (lane 0 writes)
 //   kExact  false: max via FMNMX (short dependency chain); exact while every cost is
-//           finite, which `fin` tracks (it turns NaN as soon as one is not).
+//           finite, which `fin` tracks.
 //           true: the reference's compare-select, bit-for-bit also for NaN/Inf input.
 template <int C, int NR, bool kEdge, bool kVec, bool kExact>
-__device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float (&fin)[C], const float *trow, int S,
-                                        float &carry_v, int &carry_o, const float *bin_v, const int *bin_o,
-                                        float *bout_v, int *bout_o, uint32_t *brow, int y, int x0, int lane)
+__device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *trow,
+                                        int S, int bit0, float &carry_v, int &carry_o, const float *bin_v,
+                                        const int *bin_o, float *bout_v, int *bout_o, int y, int x0, bool lane0,
+                                        bool lane31)
 {
-    constexpr int WPR = kDpWarps * C;
     float cost[NR][C];
     float lv[NR + 1];
     int lo[NR + 1];
@@ -150,11 +158,17 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float (&fi
     for (int i = 0; i < NR; ++i) {
         float up_v = __shfl_up_sync(kFullMask, v[C - 1], 1);
         int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
-        if (lane == 0) {
+        if (lane0) {
             up_v = lv[i];
             up_o = lo[i];
         }
-        uint32_t words[C];
+        if (!kExact) {
+            // non-finite detection: a product / multiply-add is NaN or Inf as soon as a factor is
+            // (a finite overflow is a harmless false positive: it only selects the exact pass)
+#pragma unroll
+            for (int k = 0; k + 1 < C; k += 2) fin = fmaf(cost[i][k], cost[i][k + 1], fin);
+            if (C & 1) fin = fmaf(cost[i][C - 1], 0.0f, fin);
+        }
 #pragma unroll
         for (int k = C - 1; k >= 0; --k) {
             const float v_prev = (k == 0) ? up_v : v[k - 1];  // value[y-1, x-1]  (core.pyx:21-27)
@@ -163,12 +177,10 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float (&fi
             // Cython's max(v_prev, v_cur) is (v_cur > v_prev) ? v_cur : v_prev; with no NaN in
             // flight that is fmaxf (one FMNMX instead of FSETP -> FSEL on the dependency chain)
             float m;
-            if (kExact) {
+            if (kExact)
                 m = (v_cur > v_prev) ? v_cur : v_prev;
-            } else {
+            else
                 m = fmaxf(v_prev, v_cur);
-                fin[k] = fmaf(cost[i][k], 0.0f, fin[k]);  // NaN iff some cost was NaN or +-Inf
-            }
             // backtrack rule, core.pyx:32: index == y or value[y-1,x] < value[y-1,x-1]
             // (the "index != 0" guard is applied by the backtrack itself)
             bool diag = v_cur < v_prev;
@@ -182,23 +194,12 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float (&fi
             }
             v[k] = nv;
             org[k] = no;
-            words[k] = __ballot_sync(kFullMask, diag);
+            if (diag) wl[k] |= 1u << (bit0 + i);
         }
         ov[i] = v[C - 1];
         oo[i] = org[C - 1];
-        if (lane == 0) {
-            uint32_t *dst = brow + (size_t)i * WPR;
-            if (C == 2) {
-                *reinterpret_cast<uint2 *>(dst) = make_uint2(words[0], words[1]);
-            } else if (C == 4) {
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < C; ++k) dst[k] = words[k];
-            }
-        }
     }
-    if (lane == 31) {
+    if (lane31) {
         if (NR == 4) {
             *reinterpret_cast<float4 *>(bout_v) = make_float4(ov[0], ov[1], ov[2], ov[3]);
             *reinterpret_cast<int4 *>(bout_o) = make_int4(oo[0], oo[1], oo[2], oo[3]);
@@ -214,34 +215,31 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float (&fi
     carry_o = lo[NR];
 }
 
+// one chunk (<= R rows) of this warp's columns; bin/bout point at the ring slot of the chunk's first row
 template <int C, bool kEdge, bool kVec, bool kExact>
-__device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float (&fin)[C], const float *tile, int S,
-                                         int rows, int row0,
-                                         int ring_mask, float &carry_v, int &carry_o, const float *bin_v,
-                                         const int *bin_o, float *bout_v, int *bout_o, uint32_t *bits_w, int x0,
-                                         int lane)
+__device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *tile,
+                                         int S, int rows, int row0, float &carry_v, int &carry_o, const float *bin_v,
+                                         const int *bin_o, float *bout_v, int *bout_o, int x0, bool lane0, bool lane31)
 {
-    constexpr int WPR = kDpWarps * C;
+    constexpr int R = dp_chunk_rows(C);
     // Threads whose columns lie past S re-read the last real columns instead of whatever
     // follows the row: their results are never used, but they must not invent NaNs.
     // (A thread straddling S reads at most C-1 floats of the next row, or of the zeroed
     // pad the producer keeps behind every tile.)
     const float *trow = tile + (x0 < S ? x0 : S - C);
-    uint32_t *brow = bits_w + (size_t)row0 * WPR;
-    int r = 0;
-    for (; r + 4 <= rows; r += 4) {
-        const int slot = (row0 + r) & ring_mask;
-        dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
-                                   bout_o + slot, brow, row0 + r, x0, lane);
-        trow += (size_t)4 * S;
-        brow += 4 * WPR;
-    }
-    for (; r < rows; ++r) {
-        const int slot = (row0 + r) & ring_mask;
-        dp_rows<C, 1, kEdge, kVec, kExact>(v, org, fin, trow, S, carry_v, carry_o, bin_v + slot, bin_o + slot, bout_v + slot,
-                                   bout_o + slot, brow, row0 + r, x0, lane);
-        trow += S;
-        brow += WPR;
+    if (rows == R) {
+#pragma unroll
+        for (int r = 0; r < R; r += 4)
+            dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, wl, trow + (size_t)r * S, S, r, carry_v, carry_o, bin_v + r,
+                                               bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
+    } else {
+        int r = 0;
+        for (; r + 4 <= rows; r += 4)
+            dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, wl, trow + (size_t)r * S, S, r, carry_v, carry_o, bin_v + r,
+                                               bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
+        for (; r < rows; ++r)
+            dp_rows<C, 1, kEdge, kVec, kExact>(v, org, fin, wl, trow + (size_t)r * S, S, r, carry_v, carry_o, bin_v + r,
+                                               bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
     }
 }
 
@@ -257,7 +255,7 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
     int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
     unsigned char *zero_s = smem + p.off_zero;
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kMaxStages; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
     }
     // ring 0 stands in for "the warp left of warp 0": column -1 is the -1e9 sentinel (core.pyx:24)
@@ -279,10 +277,10 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int T = p.T, S = p.S, R = p.R;
+    const int T = p.T, S = p.S;
+    constexpr int R = dp_chunk_rows(C);
     const int t_y = p.t_ys[b], t_x = p.t_xs[b];
     constexpr int S_pad = kDpThreads * C;
-    constexpr int WPR = kDpWarps * C;
     const int esize = path_elem_size(p.path_dtype);
     const size_t plane = (size_t)T * S;
     unsigned char *path_b = p.path + (size_t)b * plane * esize;
@@ -306,6 +304,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     }
 
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    // decision bits: word [(y >> 5) * S_pad + x], bit (y & 31)
     uint32_t *bits = p.bits_in_smem ? reinterpret_cast<uint32_t *>(smem + p.off_bits)
                                     : p.bits_ws + (size_t)slot * p.bits_words_per_cta;
     unsigned char *hop = p.hop_in_smem ? (smem + p.off_hop) : p.hop_ws + (size_t)slot * p.hop_bytes_per_cta;
@@ -316,14 +315,14 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     uint16_t *entry_s = reinterpret_cast<uint16_t *>(smem + p.off_entry);
     unsigned char *zero_s = smem + p.off_zero;
 
-    const int ring = 2 * R;
+    constexpr int ring = 2 * R;
+    const uint32_t n_stages = (uint32_t)p.stages;
     int *nonfinite_s = reinterpret_cast<int *>(smem + p.off_misc);
     if (tid == 0) *nonfinite_s = 0;
     bar_sync(kDpBar, kThreads);  // previous utterance's backtrack is done with the shared buffers
 
     const int n_chunks = (t_y + R - 1) / R;
     const int n_steps = n_chunks + kDpWarps - 1;
-    const int ring_mask = ring - 1;
     const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
     const size_t total_bytes = (size_t)p.B * plane * 4;
 
@@ -331,12 +330,13 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     // forward DP with the reference's exact compare-select (NaN/Inf semantics of core.pyx).
     int passes = 0;
     for (int pass = 0; pass < 2; ++pass) {
-        const uint32_t g0 = g_base + (uint32_t)pass * n_chunks;  // running tile number: stage = g % kStages, parity = (g / kStages) & 1
+        const uint32_t g0 = g_base + (uint32_t)pass * n_chunks;  // running tile number: stage = g % stages, parity = (g / stages) & 1
         bool saw_nonfinite = false;
         if (warp == kDpWarps) {
             // =================== producer warp ===================
             auto issue_tile = [&](int c) {
                 const uint32_t g = g0 + c;
+                const uint32_t st = g % n_stages;
                 const int row0 = c * R;
                 const int rows = min(R, t_y - row0);
                 if (p.flags && pass == 0 && (row0 & 127) == 0) {
@@ -351,7 +351,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                 const size_t src0 = start - mis;
                 const uint32_t want = mis + (uint32_t)rows * S * 4;
                 uint32_t bulk = (want + 15u) & ~15u;
-                unsigned char *dst = smem + p.off_stage + (size_t)(g % kStages) * p.stage_bytes;
+                unsigned char *dst = smem + p.off_stage + (size_t)st * p.stage_bytes;
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(p.neg_cent) + src0;
                 // finite pad behind the tile for the one thread whose columns straddle S
                 *reinterpret_cast<uint4 *>(dst + ((want + 15u) & ~15u)) = make_uint4(0, 0, 0, 0);
@@ -363,11 +363,11 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         *reinterpret_cast<float *>(dst + o) =
                             (o < want) ? *reinterpret_cast<const float *>(src + o) : 0.0f;
                 }
-                mbar_arrive_expect_tx(&full[g % kStages], bulk);
-                if (bulk) bulk_g2s(dst, src, bulk, &full[g % kStages]);
+                mbar_arrive_expect_tx(&full[st], bulk);
+                if (bulk) bulk_g2s(dst, src, bulk, &full[st]);
             };
             if (lane == 0) {
-                const int pre = min(kStages, n_chunks);
+                const int pre = min((int)n_stages, n_chunks);
                 for (int c = 0; c < pre; ++c) issue_tile(c);
             }
             // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
@@ -392,20 +392,23 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                 }
                 bar_sync(kDpBar, kThreads);
                 const int freed = step - (kDpWarps - 1);
-                if (lane == 0 && freed >= 0 && freed + kStages < n_chunks) issue_tile(freed + kStages);
+                if (lane == 0 && freed >= 0 && freed + (int)n_stages < n_chunks) issue_tile(freed + (int)n_stages);
             }
             if (pass == 0 && bulk_ok && lane == 0) bulk_wait_all();  // zeros land before the ones are scattered
         } else {
             // =================== DP warps ===================
             const int w = warp;
             const int x0 = (w * 32 + lane) * C;
-            float v[C], fin[C];
+            const bool lane0 = lane == 0, lane31 = lane == 31;
+            float v[C], fin = 0.0f;
             int org[C];
+            uint32_t wl[C], wacc[C];
 #pragma unroll
             for (int k = 0; k < C; ++k) {
                 v[k] = kNeg;
                 org[k] = x0 + k;
-                fin[k] = 0.0f;
+                wl[k] = 0u;
+                wacc[k] = 0u;
             }
             // value left of column x0 for the first row: 0 for column 0 at y == 0 (core.pyx:22-23)
             float carry_v = (w == 0) ? 0.0f : kNeg;
@@ -414,22 +417,23 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             const int *bin_o = bnd_o + (size_t)w * ring;
             float *bout_v = bnd_v + (size_t)(w + 1) * ring;
             int *bout_o = bnd_o + (size_t)(w + 1) * ring;
-            uint32_t *bits_w = bits + w * C;
             const int edge_rows = (w + 1) * 32 * C;  // rows where a column of this warp is still above the diagonal
             for (int step = 0; step < n_steps; ++step) {
                 const int c = step - w;
                 if (c >= 0 && c < n_chunks) {
                     const uint32_t g = g0 + c;
+                    const uint32_t st = g % n_stages;
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
+                    const int slot0 = (c & 1) * R;
                     const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
-                    const float *tile = reinterpret_cast<const float *>(smem + p.off_stage +
-                                                                        (size_t)(g % kStages) * p.stage_bytes + mis);
-                    mbar_wait(&full[g % kStages], (uint32_t)(g / kStages) & 1u);
+                    const float *tile =
+                        reinterpret_cast<const float *>(smem + p.off_stage + (size_t)st * p.stage_bytes + mis);
+                    mbar_wait(&full[st], (g / n_stages) & 1u);
                     const bool edge = row0 < edge_rows;
-#define MAS_CHUNK(EDGE, EXACT)                                                                                    \
-    dp_chunk<C, EDGE, kVec, EXACT>(v, org, fin, tile, S, rows, row0, ring_mask, carry_v, carry_o, bin_v, bin_o, \
-                                   bout_v, bout_o, bits_w, x0, lane)
+#define MAS_CHUNK(EDGE, EXACT)                                                                             \
+    dp_chunk<C, EDGE, kVec, EXACT>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o, bin_v + slot0, \
+                                   bin_o + slot0, bout_v + slot0, bout_o + slot0, x0, lane0, lane31)
                     if (pass == 0) {
                         if (edge)
                             MAS_CHUNK(true, false);
@@ -442,26 +446,53 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                             MAS_CHUNK(false, true);
                     }
 #undef MAS_CHUNK
+                    // decision words: R < 32 accumulates 32 / R chunks per word
+                    const int end_row = row0 + rows;
+                    const bool word_done = ((end_row & (kCheck - 1)) == 0) || (c == n_chunks - 1);
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        if (R == kCheck)
+                            wacc[k] = wl[k];
+                        else
+                            wacc[k] |= wl[k] << (row0 & (kCheck - 1));
+                        wl[k] = 0u;
+                    }
+                    if (word_done) {
+                        uint32_t *wrow = bits + (size_t)((end_row - 1) >> 5) * S_pad + x0;
+                        if (C % 4 == 0) {
+#pragma unroll
+                            for (int k = 0; k < C; k += 4)
+                                *reinterpret_cast<uint4 *>(wrow + k) =
+                                    make_uint4(wacc[k], wacc[k + 1], wacc[k + 2], wacc[k + 3]);
+                        } else if (C % 2 == 0) {
+#pragma unroll
+                            for (int k = 0; k < C; k += 2)
+                                *reinterpret_cast<uint2 *>(wrow + k) = make_uint2(wacc[k], wacc[k + 1]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < C; ++k) wrow[k] = wacc[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < C; ++k) wacc[k] = 0u;
+                    }
                     // checkpoint after rows 31, 63, ...: remember where each column backtracks to, restart origins
-                    if (((row0 + rows) & (kCheck - 1)) == 0) {
-                        unsigned char *hrow = hop + (size_t)((row0 + rows) / kCheck) * S_pad;
+                    if ((end_row & (kCheck - 1)) == 0) {
+                        unsigned char *hrow = hop + (size_t)(end_row / kCheck) * S_pad;
 #pragma unroll
                         for (int k = 0; k < C; ++k) {
                             hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
                             org[k] = x0 + k;
                         }
                         // the right-hand warp must see the restarted origin of our last column
-                        if (lane == 31) bout_o[(row0 + rows - 1) & ring_mask] = x0 + C - 1;
+                        if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
                     }
                 }
                 bar_sync(kDpBar, kThreads);
             }
             // origin of the last row relative to its checkpoint -> hop row 0
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-                hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
-                saw_nonfinite = saw_nonfinite || (fin[k] != fin[k]);
-            }
+            for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
+            saw_nonfinite = !(fabsf(fin) <= 3.0e38f);  // NaN or Inf
         }
         if (saw_nonfinite) *nonfinite_s = 1;
         bar_sync(kDpBar, kThreads);
@@ -500,9 +531,8 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         }
         for (int y = y_top; y >= y_lo; --y) {
             idx_s[y] = (uint16_t)cur;
-            const int q = cur / C;
-            const uint32_t wd = bits[(size_t)y * WPR + (q >> 5) * C + (cur - q * C)];
-            cur -= (cur != 0) ? (int)((wd >> (q & 31)) & 1u) : 0;  // core.pyx:32 "index != 0 and ..."
+            const uint32_t wd = bits[(size_t)(y >> 5) * S_pad + cur];
+            cur -= (cur != 0) ? (int)((wd >> (y & 31)) & 1u) : 0;  // core.pyx:32 "index != 0 and ..."
         }
     }
     for (int x = tid; x < S_pad; x += kThreads) end_s[x] = -1;
@@ -527,7 +557,6 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         }
     }
 }
-
 
 // host side (mas_dp.cu)
 size_t dp_workspace_bytes(int B, int T, int S);
