@@ -138,6 +138,11 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
 int mas_expand_path(const int32_t *idx, void *path_out, int path_dtype,
                     int B, int T, int S, void *stream);
 
+/* diagnostics: with MAS_TRACE=1 in the environment the fused kernel records device timestamps
+ * (ns, %globaltimer) of tile publications and DP milestones; this copies the first n_words of the
+ * trace to the host (synchronises the device).  MAS_ERR_NULL_POINTER when tracing is off. */
+int mas_debug_read_trace(unsigned long long *host_out, int n_words);
+
 /* number of kernels this library launched on the calling thread since the
  * last call (bench.py's gpu_launches); resets the counter. */
 long mas_take_launch_count(void);

@@ -23,9 +23,16 @@ for mask in masks:
     os.environ["MAS_TC_DEBUG"] = str(mask)
     for i in range(3): run(i)
     torch.cuda.synchronize()
+    # one CUDA graph of 6 calls (2 per buffer set): GPU time only, no host launch overhead
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        st = torch.cuda.current_stream().cuda_stream
+        for i in range(6): run(i)
+    st = torch.cuda.current_stream().cuda_stream
+    g.replay(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for i in range(20): run(i)
+    for _ in range(5): g.replay()
     b.record(); torch.cuda.synchronize()
-    print(f"MAS_TC_DEBUG={mask}: {a.elapsed_time(b)/20*1e3:.1f} us/call (prior images + contraction)")
+    print(f"MAS_TC_DEBUG={mask}: {a.elapsed_time(b)/30*1e3:.1f} us/call (prior images + contraction, graph replay)")
 os.environ["MAS_TC_DEBUG"] = "0"

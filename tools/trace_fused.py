@@ -1,0 +1,46 @@
+"""MAS_TRACE=1 python tools/trace_fused.py: timeline of one fused step (tile publications, DP waits)."""
+import os, sys, ctypes
+os.environ["MAS_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import torch_tts_b200 as tts
+from torch_tts_b200 import synthetic, _lib
+B, S, T, D = 64, 256, 1024, 192
+dev = torch.device("cuda:0")
+t_x, t_y = synthetic.full_lengths(B, S, T)
+z, m, l, _, _ = synthetic.prior_inputs(B, S, T, t_x, t_y, D, seed=0)
+plan = tts.AlignPlan(B, D, T, S, dev)
+args = (z.to(dev), m.to(dev), l.to(dev), t_y.to(dev), t_x.to(dev))
+L = _lib.lib()
+for _ in range(3):
+    plan.run(*args)
+torch.cuda.synchronize()
+# clear trace, run once
+buf = np.zeros(1 << 16, dtype=np.uint64)
+plan.run(*args); torch.cuda.synchronize()
+rc = L.mas_debug_read_trace(buf.ctypes.data_as(ctypes.c_void_p), buf.size)
+assert rc == 0, rc
+gem = buf[:8192].reshape(128, 64)
+dp = buf[8192:8192 + B * 32].reshape(B, 32).astype(np.int64)
+t0 = dp[:, 0].min()
+# counts accumulate over the 4 runs: last run's publications are the last (count/4) entries... use modular layout
+cnt = gem[:, 0].astype(np.int64)
+print("gemm ctas with publications:", (cnt > 0).sum(), "counts:", np.unique(cnt))
+rel = lambda x: (x - t0) / 1e3
+NRUN = 4
+rows = []
+for c in range(128):
+    k = int(cnt[c]) // NRUN
+    if k == 0: continue
+    tt = gem[c, 1 + (NRUN - 1) * k: 1 + NRUN * k].astype(np.int64)
+    rows.append(rel(tt))
+mx = max(len(r) for r in rows)
+for j in range(mx):
+    col = np.array([r[j] for r in rows if len(r) > j])
+    print(f"gemm publication {j}: n={len(col):3d} min {col.min():7.1f} mean {col.mean():7.1f} max {col.max():7.1f}")
+print("DP start  (us rel): min %.1f max %.1f" % (rel(dp[:, 0]).min(), rel(dp[:, 0]).max()))
+for k in range(8):
+    a = rel(dp[:, 2 + k])
+    print(f"tile {k} acquired: min {a.min():7.1f} mean {a.mean():7.1f} max {a.max():7.1f}")
+print("forward end: min %.1f mean %.1f max %.1f" % (rel(dp[:, 1]).min(), rel(dp[:, 1]).mean(), rel(dp[:, 1]).max()))
+print("outputs end: min %.1f mean %.1f max %.1f" % (rel(dp[:, 30]).min(), rel(dp[:, 30]).mean(), rel(dp[:, 30]).max()))

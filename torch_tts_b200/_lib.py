@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "mas_maximum_path_workspace_bytes", "mas_maximum_path_f32",
     "mas_neg_cent_workspace_bytes", "mas_neg_cent_f32",
     "mas_fused_align_workspace_bytes", "mas_fused_align_f32",
-    "mas_expand_path", "mas_take_launch_count",
+    "mas_expand_path", "mas_take_launch_count", "mas_debug_read_trace",
 )
 
 PATH_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.int32: 3}
@@ -66,6 +66,8 @@ def lib():
                 L.mas_fused_align_f32.restype = i32
                 L.mas_fused_align_f32.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp, i32, vp, vp, vp, vp, vp, sz,
                                                   i32, i32, i32, i32, vp]
+                L.mas_debug_read_trace.restype = i32
+                L.mas_debug_read_trace.argtypes = [vp, i32]
                 L.mas_expand_path.restype = i32
                 L.mas_expand_path.argtypes = [vp, vp, i32, i32, i32, i32, vp]
                 _lib = L

@@ -13,6 +13,21 @@ static thread_local char g_cuda_err[256] = "";
 
 void note_launch(int n) { g_launches += n; }
 
+unsigned long long *trace_buffer()
+{
+    static unsigned long long *buf = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char *e = getenv("MAS_TRACE");
+        if (e && *e && atoi(e)) {
+            if (cudaMalloc(&buf, kTraceWords * sizeof(unsigned long long)) != cudaSuccess) buf = nullptr;
+            if (buf) cudaMemset(buf, 0, kTraceWords * sizeof(unsigned long long));
+        }
+    }
+    return buf;
+}
+
 int note_cuda_error(cudaError_t e, const char *what)
 {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
@@ -182,6 +197,15 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
     }
     return dp_launch(nc, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T, S,
                      st);
+}
+
+int mas_debug_read_trace(unsigned long long *host_out, int n_words)
+{
+    unsigned long long *buf = trace_buffer();
+    if (!buf || !host_out) return MAS_ERR_NULL_POINTER;
+    if (n_words > kTraceWords) n_words = kTraceWords;
+    MAS_CUDA_TRY(cudaMemcpy(host_out, buf, (size_t)n_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return MAS_OK;
 }
 
 int mas_expand_path(const int32_t *idx, void *path_out, int path_dtype, int B, int T, int S, void *stream)

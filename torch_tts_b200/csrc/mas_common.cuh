@@ -17,6 +17,9 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 // ---- host-side bookkeeping (defined in mas_api.cu) -------------------------
 void note_launch(int n = 1);
+// MAS_TRACE=1: device buffer of kTraceWords timestamps the fused kernel fills (diagnostics), else nullptr
+unsigned long long *trace_buffer();
+constexpr int kTraceWords = 1 << 16;
 int note_cuda_error(cudaError_t e, const char *what);
 
 #define MAS_CUDA_TRY(expr)                                        \
@@ -114,10 +117,20 @@ __device__ __forceinline__ void tma_store_3d(const void *tmap, int c0, int c1, i
                  ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src_smem))
                  : "memory");
 }
+// pull a 3-D tile into L2 only (no shared-memory destination, no completion)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void *tmap, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
+// wait until at most N bulk groups are still pending at all (their global writes have landed)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // wait until at most N bulk groups still READ their shared-memory source
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -134,6 +147,13 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
     return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // named barrier over `count` threads (count a multiple of 32); id 0 is __syncthreads()
 __device__ __forceinline__ void bar_sync(int id, int count)

@@ -77,12 +77,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_cost_tc_kernel(const TcPara
                                                                     const __grid_constant__ CUtensorMap tm_out)
 {
     extern __shared__ unsigned char smem_raw[];
-    cost_tc_role<kStats>(p, &tm_z, &tm_out, smem_raw, blockIdx.x, gridDim.x);
+    cost_tc_role<kStats, false>(p, &tm_z, &tm_out, smem_raw, blockIdx.x, gridDim.x);
+}
+
+// CTA-pair version: clusters of 2, one M = 256 cta_group::2 MMA per pair
+template <bool kStats>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+    mas_cost_tc_pair_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_z,
+                            const __grid_constant__ CUtensorMap tm_out)
+{
+    extern __shared__ unsigned char smem_raw[];
+    cost_tc_role<kStats, true>(p, &tm_z, &tm_out, smem_raw, blockIdx.x >> 1, gridDim.x >> 1);
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// MAS_TC_PAIR=0 selects the single-CTA (cta_group::1) contraction
+bool cost_tc_pair_enabled()
+{
+    const char *e = getenv("MAS_TC_PAIR");
+    return !(e && *e && atoi(e) == 0);
+}
+
 bool cost_tc_supported(int B, int D, int T, int S)
 {
     (void)B;
@@ -106,10 +123,13 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
     unsigned char *images = static_cast<unsigned char *>(workspace);
     float *bias = reinterpret_cast<float *>(images + align_up((size_t)B * n_kb * 2 * kBPart, 256));
     if (stats_out) MAS_CUDA_TRY(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double), stream));
-    mas_prior_images_kernel<<<dim3(n_kb, B), kNMax, 0, stream>>>(m_p, logs_p, images, bias, D, S, n_kb, flags_to_clear,
-                                                                 n_flags);
-    note_launch();
-    MAS_CUDA_TRY(cudaGetLastError());
+    const char *dbg = getenv("MAS_TC_DEBUG");  // bit 16: reuse the images already in the workspace (timing experiments)
+    if (!(dbg && *dbg && (atoi(dbg) & 16))) {
+        mas_prior_images_kernel<<<dim3(n_kb, B), kNMax, 0, stream>>>(m_p, logs_p, images, bias, D, S, n_kb,
+                                                                     flags_to_clear, n_flags);
+        note_launch();
+        MAS_CUDA_TRY(cudaGetLastError());
+    }
 
     TcParams &p = plan.p;
     p = TcParams{};
@@ -127,6 +147,7 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
     p.n_cols = (S + 15) / 16 * 16;
     p.m_tiles = (T + kBM - 1) / kBM;
     p.wave = B;
+    p.trace = trace_buffer();
     const char *e = getenv("MAS_TC_DEBUG");
     p.debug = (e && *e) ? atoi(e) : 0;
     const char *nt = getenv("MAS_TC_NO_TMA");  // A-B experiments: bit 1 plain z loads, bit 2 plain output stores
@@ -155,19 +176,31 @@ int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, floa
                                           (int)kTcSmem));
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_cost_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kTcSmem));
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_cost_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kTcSmem));
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_cost_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kTcSmem));
         configured_dev = dev;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int n_tiles = B * plan.p.m_tiles;
-    int grid = n_tiles < sms ? n_tiles : sms;
-    {
-        const char *g = getenv("MAS_TC_GRID");  // experiments: restrict the contraction to fewer SMs
-        if (g && *g && atoi(g) > 0 && atoi(g) < grid) grid = atoi(g);
+    const char *g = getenv("MAS_TC_GRID");  // experiments: restrict the contraction to fewer SMs
+    if (g && *g && atoi(g) > 0 && atoi(g) < sms) sms = atoi(g);
+    if (plan.p.debug & 8) return MAS_OK;  // timing experiments: prior preparation only
+    if (cost_tc_pair_enabled()) {
+        const int n_units = B * ((plan.p.m_tiles + 1) / 2);
+        int grid = 2 * n_units < sms ? 2 * n_units : (sms & ~1);
+        if (stats_out)
+            mas_cost_tc_pair_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
+        else
+            mas_cost_tc_pair_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
+    } else {
+        const int n_tiles = B * plan.p.m_tiles;
+        const int grid = n_tiles < sms ? n_tiles : sms;
+        if (stats_out)
+            mas_cost_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
+        else
+            mas_cost_tc_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
     }
-    if (stats_out)
-        mas_cost_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
-    else
-        mas_cost_tc_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
     note_launch();
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;

@@ -14,15 +14,16 @@
 // reference's own fp32 sgemm noise level), at the cost of 3 bf16 passes = 1.5 TF32 passes
 // instead of the 3 a 3xTF32 split needs.
 //
-// CTA layout (12 warps, one CTA per SM, persistent over a static tile list):
+// CTA layout (16 warps, one CTA per SM, persistent over a static tile list):
 //   warp 0      B producer: 1-D TMA bulk copies of the pre-swizzled B images -> smem
 //   warp 3      z producer: TMA tensor loads of raw z_p tiles [16 ch x 128 mel] -> smem
 //   warp 1      MMA issuer: one thread issues tcgen05.mma, commits to mbarriers
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue: tcgen05.ld accumulator -> + bias -> swizzled smem -> TMA tensor store
 //               (and the noise statistics); publishes the tile flag in the fused kernel
-//   warps 8-11  A converters: raw z (smem) -> -0.5 z^2, z -> bf16 hi/lo -> K-major
-//               SWIZZLE_64B operand tiles in smem
+//   warps 8-15  A converters, two groups of 4 warps taking alternate K blocks (a K block is a
+//               latency chain: wait -> LDS -> split -> STS -> fence -> arrive): raw z (smem) ->
+//               -0.5 z^2, z -> bf16 hi/lo -> K-major SWIZZLE_64B operand tiles in smem
 // Tile = 128 mel rows x N text columns (N = S rounded up to 16, <= 256); K blocks of 32 bf16
 // (16 prior channels): 3 operand stages of 48 KB, 4 raw-z stages of 8 KB, 2 TMEM accumulators.
 #pragma once
@@ -33,25 +34,33 @@
 
 namespace mas {
 
-constexpr int kTcThreads = 384;
+constexpr int kTcThreads = 512;
 constexpr int kBM = 128;            // mel rows per tile (UMMA M)
 constexpr int kBK = 32;             // bf16 K elements per block (= one 64-byte swizzle row)
 constexpr int kDPerKb = kBK / 2;    // prior channels per K block
 constexpr int kNMax = 256;          // text columns per tile (UMMA N max)
-constexpr int kTcStages = 3;        // operand stages
-constexpr int kZStages = 4;         // raw z stages
 constexpr uint32_t kRowBytes = kBK * 2;               // 64
 constexpr uint32_t kAPart = kBM * kRowBytes;          // 8 KB: one split part of A per stage
-constexpr uint32_t kBPart = kNMax * kRowBytes;        // 16 KB: one split part of B per stage / per image
-constexpr uint32_t kStageBytes = 2 * kAPart + 2 * kBPart;   // 48 KB
+constexpr uint32_t kBPart = kNMax * kRowBytes;        // 16 KB: one split part of B per image
 constexpr uint32_t kZStageBytes = kDPerKb * kBM * 4;        // 8 KB
 constexpr uint32_t kEpiBufBytes = 32 * 128;                 // 32 rows x 32 fp32, SWIZZLE_128B
-constexpr uint32_t kTcOffZ = kTcStages * kStageBytes;
-constexpr uint32_t kTcOffEpi = kTcOffZ + kZStages * kZStageBytes;
-constexpr uint32_t kTcOffBias = kTcOffEpi + 8 * kEpiBufBytes;
-constexpr uint32_t kTcOffBar = kTcOffBias + kNMax * 4;
-constexpr uint32_t kTcSmemUsed = kTcOffBar + 256;
-constexpr uint32_t kTcSmem = kTcSmemUsed + 1024 /*alignment slack*/;
+
+// shared-memory layout of the role.  kPair: two CTAs of a cluster run one M = 256 tcgen05.mma
+// (cta_group::2); each holds its own 128 A rows and HALF of the B rows, so the B bytes every SM
+// pulls out of L2 -- the bound of the single-CTA version -- are halved.
+template <bool kPair>
+struct TcCfg {
+    static constexpr int kStages = kPair ? 4 : 3;                          // operand stages
+    static constexpr int kZStages = kPair ? 6 : 5;                         // raw z stages (bytes in flight towards HBM)
+    static constexpr uint32_t kBPartS = kPair ? kBPart / 2 : kBPart;       // bytes of one B part in a stage
+    static constexpr uint32_t kStage = 2 * kAPart + 2 * kBPartS;           // 32 KB / 48 KB
+    static constexpr uint32_t kOffZ = kStages * kStage;
+    static constexpr uint32_t kOffEpi = kOffZ + kZStages * kZStageBytes;
+    static constexpr uint32_t kOffBias = kOffEpi + 8 * kEpiBufBytes;
+    static constexpr uint32_t kOffBar = kOffBias + 2 * kNMax * 4;  // two bias buffers
+    static constexpr uint32_t kSmem = kOffBar + 512 + 1024 /*alignment slack*/;
+};
+constexpr uint32_t kTcSmem = TcCfg<false>::kSmem > TcCfg<true>::kSmem ? TcCfg<false>::kSmem : TcCfg<true>::kSmem;
 
 // ---- PTX: tcgen05 ------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols)
@@ -84,6 +93,74 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants -------------------------------------------
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at the same offset in BOTH CTAs of the pair once the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_2cta(uint64_t *bar)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    // default semantics (.release.cta): an explicit .release.cluster costs a MEMBAR.ALL.GPU per arrive.  The
+    // data this orders stays in the arriving SM's own shared memory (its tensor core reads it), as in
+    // CUTLASS's ClusterBarrier::arrive(cta_id).
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local mbarrier that is also arrived on by the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32])
 {
     asm volatile(
@@ -112,10 +189,10 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr)
     return d;
 }
 
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int n)
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = m (128, or 256 for a CTA pair), N = n
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // byte offset of element (row, k) inside a K-major SWIZZLE_64B bf16 tile (row pitch 64 B):
@@ -155,20 +232,23 @@ struct TcParams {
     int m_tiles;                   // ceil(T / 128)
     int wave;                      // tile order: utterances in groups of `wave`, mel-tile-major inside a group
     int z_tma, out_tma;            // tensor maps usable (T % 4 == 0 / S % 4 == 0)
-    int debug;                     // MAS_TC_DEBUG bit mask (profiling experiments): 1 no A stores, 2 no epilogue stores, 4 no MMA
+    unsigned long long *trace;     // nullable diagnostics buffer: [cta][64] publication times
+    int debug;                     // MAS_TC_DEBUG bit mask (profiling experiments): 1 no A stores, 2 no epilogue stores, 4 no MMA,
+                                   // 32 no z loads, 64 no B loads (8 / 16 on the host: prior only / contraction only)
 };
 
-// tile order index -> (b, mt); utterance groups of p.wave, mel-tile-major inside a group, so that in
-// the fused kernel every utterance of a group receives its first tiles early
-__device__ __forceinline__ void tc_tile_coords(const TcParams &p, int i, int &b, int &mt)
+// work-unit order index -> (b, mu); utterance groups of p.wave, mel-major inside a group, so that in
+// the fused kernel every utterance of a group receives its first tiles early.  A unit is one mel
+// tile (single CTA) or a pair of adjacent mel tiles (CTA pair): m_units per utterance.
+__device__ __forceinline__ void tc_unit_coords(const TcParams &p, int m_units, int i, int &b, int &mu)
 {
-    const int per_wave = p.wave * p.m_tiles;
+    const int per_wave = p.wave * m_units;
     const int w = i / per_wave;
     const int r = i - w * per_wave;
     const int base = w * p.wave;
     const int wc = min(p.wave, p.B - base);
-    mt = r / wc;
-    b = base + (r - mt * wc);
+    mu = r / wc;
+    b = base + (r - mu * wc);
 }
 
 __device__ __forceinline__ bool tc_tile_live(const TcParams &p, int b, int mt)
@@ -179,32 +259,44 @@ __device__ __forceinline__ bool tc_tile_live(const TcParams &p, int b, int mt)
 }
 
 // The contraction role.  Runs on all kTcThreads threads of the CTA (dynamic smem `smem_raw`,
-// at least kTcSmem bytes); processes tiles first, first + step, ... of the tile order.
-template <bool kStats>
+// at least kTcSmem bytes); processes work units first, first + step, ... of the unit order.
+// kPair: the CTA is one of a 2-CTA cluster; `first`/`step` count pairs; rank r of the pair owns mel
+// tile 2 * mu + r, holds rows [r * N/2, (r+1) * N/2) of every B stage, and rank 0 issues the MMAs.
+template <bool kStats, bool kPair>
 __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMap *tm_z, const CUtensorMap *tm_out,
                                              unsigned char *smem_raw, int first, int step)
 {
+    using Cfg = TcCfg<kPair>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kZStages = Cfg::kZStages;
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char *smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);  // swizzled tiles need 1024-byte alignment
-    float *bias_s = reinterpret_cast<float *>(smem + kTcOffBias);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTcOffBar);
-    uint64_t *full = bars;                 // [3] operand stage filled: B bytes landed + 4 converter warps arrived
-    uint64_t *empty = bars + 3;            // [3] operand stage consumed by the MMAs
-    uint64_t *zfull = bars + 6;            // [4] raw z stage landed
-    uint64_t *zempty = bars + 10;          // [4] raw z stage read by the 4 converter warps
-    uint64_t *acc_full = bars + 14;        // [2] accumulator complete
-    uint64_t *acc_empty = bars + 16;       // [2] accumulator drained by the epilogue
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 18);
+    float *bias_s = reinterpret_cast<float *>(smem + Cfg::kOffBias);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kOffBar);
+    uint64_t *full = bars;                 // [4] operand stage filled (pair: rank 0's copy collects both CTAs)
+    uint64_t *empty = bars + 4;            // [4] operand stage consumed by the MMAs
+    uint64_t *bfull = bars + 8;            // [4] pair, rank 1: own B bytes landed (forwarded to rank 0's full)
+    uint64_t *zfull = bars + 12;           // [8] raw z stage landed
+    uint64_t *zempty = bars + 20;          // [8] raw z stage read by the 4 converter warps of a group
+    uint64_t *acc_full = bars + 28;        // [2] accumulator complete
+    uint64_t *acc_empty = bars + 30;       // [2] accumulator drained by the epilogue (pair: of both CTAs)
+    uint64_t *bias_full = bars + 32;       // [2] bias buffer written by warp 2
+    uint64_t *bias_empty = bars + 34;      // [2] bias buffer released by the 4 epilogue warps
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 36);
+    uint32_t *pub_cnt = tmem_slot + 1;     // [2] epilogue warps whose stores of a unit have completed
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int n_tiles = p.B * p.m_tiles;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const int m_units = kPair ? (p.m_tiles + 1) / 2 : p.m_tiles;
+    const int n_units = p.B * m_units;
 
     if (tid == 0) {
-        for (int i = 0; i < kTcStages; ++i) {
-            mbar_init(&full[i], 1 + 4);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full[i], kPair ? 10 : 5);  // B producer + 4 converter warps (+ the peer's 4 + its forwarder)
             mbar_init(&empty[i], 1);
+            mbar_init(&bfull[i], 1);
         }
         for (int i = 0; i < kZStages; ++i) {
             mbar_init(&zfull[i], 1);
@@ -212,110 +304,225 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 4);
+            mbar_init(&acc_empty[i], kPair ? 8 : 4);
+            mbar_init(&bias_full[i], 1);
+            mbar_init(&bias_empty[i], 4);
+            pub_cnt[i] = 0u;
         }
         fence_mbar_init();
         if (p.z_tma) tma_prefetch_desc(tm_z);
         if (p.out_tma) tma_prefetch_desc(tm_out);
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) {
+        if (kPair)
+            tmem_alloc2(tmem_slot, 512);
+        else
+            tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
     bar_sync(1, kTcThreads);
+    if (kPair) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // this CTA's mel tile of unit (b, mu), and whether the unit is processed at all
+    auto unit_tile = [&](int i, int &b, int &mt) {
+        int mu;
+        tc_unit_coords(p, m_units, i, b, mu);
+        mt = kPair ? 2 * mu + (int)rank : mu;
+        return tc_tile_live(p, b, kPair ? 2 * mu : mu);
+    };
+    // diagnostics: trace[16384 + cta * 64 + role * 16 + 2 * unit + {0: begin, 1: end}], roles 0 MMA, 1 epilogue, 2 converter, 3 z
+    auto tr_mark = [&](int role, uint32_t unit, int which) {
+        if (p.trace && unit < 8) p.trace[16384 + (size_t)blockIdx.x * 64 + role * 16 + 2 * unit + which] = globaltimer_ns();
+    };
+    // rows of a B image this CTA stages, and their bytes
+    const uint32_t b_rows = kPair ? (uint32_t)p.n_cols / 2 : (uint32_t)p.n_cols;
+    const uint32_t b_bytes = b_rows * kRowBytes;
+    const uint32_t b_off = kPair ? rank * b_bytes : 0u;
+
     if (warp == 0) {
-        // ======================= producer =======================
+        // ======================= B producer =======================
         if (lane == 0) {
             uint32_t it = 0;
-            const uint32_t b_bytes = (uint32_t)p.n_cols * kRowBytes;
-            for (int i = first; i < n_tiles; i += step) {
+            for (int i = first; i < n_units; i += step) {
                 int b, mt;
-                tc_tile_coords(p, i, b, mt);
-                if (!tc_tile_live(p, b, mt)) continue;
+                if (!unit_tile(i, b, mt)) continue;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-                    const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
-                    unsigned char *stage = smem + s * kStageBytes;
-                    const unsigned char *img = p.images + (size_t)(b * p.n_kb + kb) * 2 * kBPart;
-                    mbar_arrive_expect_tx(&full[s], 2 * b_bytes);
-                    bulk_g2s(stage + 2 * kAPart, img, b_bytes, &full[s]);
-                    bulk_g2s(stage + 2 * kAPart + kBPart, img + kBPart, b_bytes, &full[s]);
+                    unsigned char *stage = smem + s * Cfg::kStage;
+                    const unsigned char *img = p.images + (size_t)(b * p.n_kb + kb) * 2 * kBPart + b_off;
+                    uint64_t *bar = (kPair && rank) ? &bfull[s] : &full[s];
+                    if (p.debug & 64) {  // experiment: no B traffic
+                        mbar_arrive(bar);
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(bar, 2 * b_bytes);
+                    bulk_g2s(stage + 2 * kAPart, img, b_bytes, bar);
+                    bulk_g2s(stage + 2 * kAPart + Cfg::kBPartS, img + kBPart, b_bytes, bar);
                 }
             }
         }
     } else if (warp == 3) {
         // ======================= raw z producer (runs ahead of the operand ring) =======================
-        if (lane == 0 && p.z_tma) {
+        if (lane == 0 && p.z_tma && !(p.debug & 32)) {
             uint32_t it = 0;
-            for (int i = first; i < n_tiles; i += step) {
+            for (int i = first; i < n_units; i += step) {
                 int b, mt;
-                tc_tile_coords(p, i, b, mt);
-                if (!tc_tile_live(p, b, mt)) continue;
+                if (!unit_tile(i, b, mt)) continue;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
                     const uint32_t zs = it % kZStages, zph = (it / kZStages) & 1u;
                     mbar_wait(&zempty[zs], zph ^ 1u);
                     mbar_arrive_expect_tx(&zfull[zs], kZStageBytes);
-                    tma_load_3d(smem + kTcOffZ + zs * kZStageBytes, tm_z, mt * kBM, kb * kDPerKb, b, &zfull[zs]);
+                    tma_load_3d(smem + Cfg::kOffZ + zs * kZStageBytes, tm_z, mt * kBM, kb * kDPerKb, b, &zfull[zs]);
                 }
             }
         }
     } else if (warp == 1) {
-        // ======================= MMA issuer =======================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(p.n_cols);
+        if (lane == 0 && rank == 0) {
+            // ======================= MMA issuer =======================
+            const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kBM : kBM, p.n_cols);
             uint32_t it = 0, nt = 0;
-            for (int i = first; i < n_tiles; i += step) {
+            for (int i = first; i < n_units; i += step) {
                 int b, mt;
-                tc_tile_coords(p, i, b, mt);
-                if (!tc_tile_live(p, b, mt)) continue;
+                if (!unit_tile(i, b, mt)) continue;
                 const uint32_t a = nt & 1u, aph = (nt >> 1) & 1u;
-                mbar_wait(&acc_empty[a], aph ^ 1u);
+                if (kPair)
+                    mbar_wait_cluster(&acc_empty[a], aph ^ 1u);
+                else
+                    mbar_wait(&acc_empty[a], aph ^ 1u);
                 tc_fence_after();
+                tr_mark(0, nt, 0);
                 const uint32_t tmem_d = tmem_base + a * kNMax;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-                    const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
-                    mbar_wait(&full[s], ph);
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    if (kPair)
+                        mbar_wait_cluster(&full[s], ph);
+                    else
+                        mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t st = smem_u32(smem + s * kStageBytes);
+                    const uint32_t st = smem_u32(smem + s * Cfg::kStage);
                     const uint64_t a_hi = make_desc_sw64(st), a_lo = make_desc_sw64(st + kAPart);
-                    const uint64_t b_hi = make_desc_sw64(st + 2 * kAPart), b_lo = make_desc_sw64(st + 2 * kAPart + kBPart);
+                    const uint64_t b_hi = make_desc_sw64(st + 2 * kAPart),
+                                   b_lo = make_desc_sw64(st + 2 * kAPart + Cfg::kBPartS);
 #pragma unroll
                     for (int k = 0; k < kBK / 16 && !(p.debug & 4); ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 16 bf16 = 32 bytes along K
-                        umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                        umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
-                        umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        if (kPair) {
+                            umma_bf16_2cta(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                            umma_bf16_2cta(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+                            umma_bf16_2cta(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        } else {
+                            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+                            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                        }
                     }
-                    umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+                    // frees the stage (in both CTAs of a pair) when these MMAs have read it
+                    if (kPair)
+                        umma_commit_2cta(&empty[s]);
+                    else
+                        umma_commit(&empty[s]);
                 }
-                umma_commit(&acc_full[a]);
+                if (kPair)
+                    umma_commit_2cta(&acc_full[a]);
+                else
+                    umma_commit(&acc_full[a]);
+                tr_mark(0, nt, 1);
                 ++nt;
             }
+        } else if (kPair && lane == 0 && rank == 1) {
+            // ======================= forwarder: own B half landed -> rank 0's full barrier =======================
+            uint32_t it = 0;
+            for (int i = first; i < n_units; i += step) {
+                int b, mt;
+                if (!unit_tile(i, b, mt)) continue;
+                for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    mbar_wait(&bfull[s], ph);
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&full[s]), 0));
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ======================= bias: sum of the K-block partials of the unit's utterance =======================
+        uint32_t n = 0;
+        for (int i = first; i < n_units; i += step, (void)0) {
+            int b, mt;
+            if (!unit_tile(i, b, mt)) continue;
+            const uint32_t buf = n & 1u, ph = (n >> 1) & 1u;
+            mbar_wait(&bias_empty[buf], ph ^ 1u);
+            const float *bp = p.bias_part + (size_t)b * p.n_kb * p.S;
+            if ((p.S & 3) == 0) {
+                // 4 columns per lane and pass, up to 12 partials in flight per lane; summed in K-block order
+                for (int s = 4 * lane; s < p.n_cols; s += 128) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s < p.S) {
+                        for (int kb0 = 0; kb0 < p.n_kb; kb0 += 12) {
+                            float4 part[12];
+#pragma unroll
+                            for (int j = 0; j < 12; ++j)
+                                part[j] = (kb0 + j < p.n_kb)
+                                              ? __ldg(reinterpret_cast<const float4 *>(bp + (size_t)(kb0 + j) * p.S + s))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int j = 0; j < 12; ++j) {
+                                acc.x += part[j].x, acc.y += part[j].y, acc.z += part[j].z, acc.w += part[j].w;
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(bias_s + buf * kNMax + s) = acc;
+                }
+            } else {
+                for (int s = lane; s < p.n_cols; s += 32) {
+                    float acc = 0.f;
+                    if (s < p.S)
+                        for (int kb = 0; kb < p.n_kb; ++kb) acc += bp[(size_t)kb * p.S + s];
+                    bias_s[buf * kNMax + s] = acc;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bias_full[buf]);
+            ++n;
         }
     } else if (warp >= 4 && warp < 8) {
         // ======================= epilogue =======================
         const int wq = warp & 3;  // TMEM lane quarter this warp may read
         const int row = wq * 32 + lane;
-        unsigned char *ebuf = smem + kTcOffEpi + wq * 2 * kEpiBufBytes;
+        unsigned char *ebuf = smem + Cfg::kOffEpi + wq * 2 * kEpiBufBytes;
         uint32_t nt = 0, nst = 0;
         double ssum = 0.0, ssq = 0.0;
-        for (int i = first; i < n_tiles; i += step) {
-            int b, mt;
-            tc_tile_coords(p, i, b, mt);
-            if (!tc_tile_live(p, b, mt)) continue;
-            // bias of this utterance -> smem (only the 4 epilogue warps sync here)
-            bar_sync(2, 128);
-            for (int s = tid - 128; s < p.n_cols; s += 128) {
-                float acc = 0.f;
-                if (s < p.S)
-                    for (int kb = 0; kb < p.n_kb; ++kb) acc += p.bias_part[((size_t)b * p.n_kb + kb) * p.S + s];
-                bias_s[s] = acc;
+        // lazily published tile flag (fused kernel): the previous unit's flag goes out once this warp's
+        // stores of it have completed, which is checked after the first store of the next unit
+        uint32_t *pend_flag = nullptr;
+        uint32_t pend_par = 0;
+        auto publish = [&](uint32_t *flag, uint32_t par) {
+            // lane 0 only; this warp's stores of the unit are complete
+            fence_proxy_async_all();
+            __threadfence_block();
+            if (atomicAdd(&pub_cnt[par], 1u) == 3u) {
+                pub_cnt[par] = 0u;
+                __threadfence();
+                st_release_gpu(flag, 1u);
+                if (p.trace) {
+                    unsigned long long *tr = p.trace + (size_t)blockIdx.x * 64;
+                    const unsigned long long n = tr[0] + 1;   // word 0: count, then one time per published tile
+                    tr[0] = n;
+                    if (n < 63) tr[n] = globaltimer_ns();
+                    if (n == 1) tr[63] = ((unsigned long long)(flag - p.flags));
+                }
             }
-            bar_sync(2, 128);
+        };
+        for (int i = first; i < n_units; i += step) {
+            int b, mt;
+            if (!unit_tile(i, b, mt)) continue;
             const uint32_t a = nt & 1u, aph = (nt >> 1) & 1u;
+            mbar_wait(&bias_full[a], aph);
+            const float *bias_u = bias_s + a * kNMax;
             mbar_wait(&acc_full[a], aph);
             tc_fence_after();
+            if (tid == 128) tr_mark(1, nt, 0);
             const int t = mt * kBM + row;
             float *orow = p.out + ((size_t)b * p.T + t) * p.S;
             const uint32_t taddr = tmem_base + a * kNMax + ((uint32_t)(wq * 32) << 16);
@@ -325,7 +532,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c0 + j];
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_u[c0 + j];
                 if (kStats) {
                     if (t < p.T) {
 #pragma unroll
@@ -350,6 +557,11 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     if (lane == 0) {
                         tma_store_3d(tm_out, c0, mt * kBM + wq * 32, b, buf);  // rows >= T / cols >= S are clipped
                         bulk_commit();
+                        if (c0 == 0 && pend_flag) {
+                            bulk_wait_group<1>();  // everything older than the store just committed has landed
+                            publish(pend_flag, pend_par);
+                            pend_flag = nullptr;
+                        }
                     }
                     ++nst;
                 } else if (t < p.T) {
@@ -359,23 +571,31 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 }
             }
             tc_fence_before();
+            if (tid == 128) tr_mark(1, nt, 1);
+            if (!p.out_tma && p.flags) __threadfence();  // plain stores of every lane, before lane 0 publishes
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
-            ++nt;
-            if (p.flags) {
-                // publish the tile: all stores of the 4 epilogue warps are complete, then release
-                if (p.out_tma) {
-                    if (lane == 0) bulk_wait_all();
-                } else {
-                    __threadfence();
-                }
-                bar_sync(2, 128);
-                if (tid == 128) {
-                    fence_proxy_async_all();
-                    __threadfence();
-                    st_release_gpu(p.flags + (size_t)b * p.m_tiles + mt, 1u);
+            if (lane == 0) {
+                mbar_arrive(&bias_empty[a]);
+                if (kPair && rank)
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[a]), 0));
+                else
+                    mbar_arrive(&acc_empty[a]);
+                if (p.flags && mt < p.m_tiles) {
+                    uint32_t *flag = p.flags + (size_t)b * p.m_tiles + mt;
+                    if (p.out_tma && !(p.debug & 2)) {
+                        pend_flag = flag;  // published after the first store of the next unit (or after the loop)
+                        pend_par = a;
+                    } else {
+                        __threadfence();
+                        publish(flag, a);
+                    }
                 }
             }
+            ++nt;
+        }
+        if (lane == 0 && pend_flag) {
+            bulk_wait_all();
+            publish(pend_flag, pend_par);
         }
         if (p.out_tma && lane == 0) bulk_wait_all();
         if (kStats) {
@@ -390,33 +610,47 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         }
     } else if (warp >= 8) {
         // ======================= A converters =======================
-        const int row = tid - 256;  // 0..127: mel row of the tile handled by this thread
+        const int grp = (warp - 8) >> 2;           // converter group: takes K blocks with (it & 1) == grp
+        const int row = (tid - 256) & (kBM - 1);    // 0..127: mel row of the tile handled by this thread
         uint32_t it = 0;
-        for (int i = first; i < n_tiles; i += step) {
+        // where this warp announces a converted stage: rank 0's full barriers (a linear window)
+        const uint32_t full0 = kPair ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
+        long long ph_acc[5] = {0, 0, 0, 0, 0};  // diagnostics: cycles in wait-z, LDS, wait-empty, convert+STS, fence+arrive
+        for (int i = first; i < n_units; i += step) {
             int b, mt;
-            tc_tile_coords(p, i, b, mt);
-            if (!tc_tile_live(p, b, mt)) continue;
+            if (!unit_tile(i, b, mt)) continue;
             const int t = mt * kBM + row;
-            const bool live = t < p.T;
+            const bool live = t < p.T && mt < p.m_tiles;
             const float *zb = p.z_p + (size_t)b * p.D * p.T + (live ? t : 0);
+            if (tid == 256) tr_mark(2, it / (uint32_t)p.n_kb, 0);
             for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+                if (tid == 256 && kb == p.n_kb - 2) tr_mark(2, it / (uint32_t)p.n_kb, 1);
+                if ((int)(it & 1u) != grp) continue;
+                const long long c0k = p.trace ? clock64() : 0;
+                long long c1k = 0, c2k = 0, c3k = 0, c4k = 0;
                 float zc[kDPerKb];
-                if (p.z_tma) {
+                if (p.debug & 32) {  // experiment: no z traffic
+#pragma unroll
+                    for (int d = 0; d < kDPerKb; ++d) zc[d] = 0.f;
+                } else if (p.z_tma) {
                     const uint32_t zs = it % kZStages, zph = (it / kZStages) & 1u;
                     mbar_wait(&zfull[zs], zph);
-                    const float *zr = reinterpret_cast<const float *>(smem + kTcOffZ + zs * kZStageBytes) + row;
+                    if (p.trace) c1k = clock64();
+                    const float *zr = reinterpret_cast<const float *>(smem + Cfg::kOffZ + zs * kZStageBytes) + row;
 #pragma unroll
                     for (int d = 0; d < kDPerKb; ++d) zc[d] = zr[d * kBM];  // zero-filled past T / D by the TMA
                     __syncwarp();
+                    if (p.trace) c2k = clock64() + (long long)(__float_as_int(zc[0]) & 0);
                     if (lane == 0) mbar_arrive(&zempty[zs]);
                 } else {
                     const int d0 = kb * kDPerKb;
 #pragma unroll
                     for (int d = 0; d < kDPerKb; ++d) zc[d] = (live && d0 + d < p.D) ? zb[(size_t)(d0 + d) * p.T] : 0.f;
                 }
-                const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
-                unsigned char *a_hi = smem + s * kStageBytes;
+                if (p.trace) c3k = clock64();
+                unsigned char *a_hi = smem + s * Cfg::kStage;
                 unsigned char *a_lo = a_hi + kAPart;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {  // chunk c: k in [8c, 8c+8); c < 2: -0.5 z^2, c >= 2: z
@@ -437,16 +671,36 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                         *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
+                if (p.trace) c4k = clock64();
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+                if (lane == 0) {
+                    if (kPair)
+                        mbar_arrive_cluster(full0 + s * 8u);
+                    else
+                        mbar_arrive(&full[s]);
+                }
+                if (p.trace) {
+                    const long long c5k = clock64();
+                    ph_acc[0] += c1k - c0k, ph_acc[1] += c2k - c1k, ph_acc[2] += c3k - c2k, ph_acc[3] += c4k - c3k,
+                        ph_acc[4] += c5k - c4k;
+                }
             }
         }
+        if (p.trace && (tid == 256 || tid == 384))
+            for (int j = 0; j < 5; ++j)
+                p.trace[32768 + (size_t)blockIdx.x * 16 + (tid == 384 ? 8 : 0) + j] = (unsigned long long)ph_acc[j];
     }
 
     tc_fence_before();
     bar_sync(1, kTcThreads);
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (kPair) cluster_sync_all();  // nothing of the peer is in flight towards this CTA any more
+    if (warp == 2) {
+        if (kPair)
+            tmem_dealloc2(tmem_base, 512);
+        else
+            tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // host side (mas_cost_tc.cu)
@@ -455,6 +709,7 @@ struct TcPlan {
     CUtensorMap tm_z, tm_out;
 };
 bool cost_tc_supported(int B, int D, int T, int S);
+bool cost_tc_pair_enabled();
 size_t cost_tc_workspace_bytes(int B, int D, int T, int S);
 // launches the prior-image preparation (which also zeroes `flags_to_clear`, n_flags words, if given)
 // and fills `plan` for the contraction

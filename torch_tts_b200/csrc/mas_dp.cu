@@ -4,6 +4,12 @@
 
 namespace mas {
 
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
 // ---------------------------------------------------------------------------
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
@@ -146,11 +152,6 @@ __global__ void mas_expand_kernel(const int32_t *__restrict__ idx, unsigned char
 // ---------------------------------------------------------------------------
 // host entry points used by mas_api.cu
 // ---------------------------------------------------------------------------
-static int env_int(const char *name, int dflt)
-{
-    const char *s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
 
 size_t dp_workspace_bytes(int B, int T, int S)
 {
@@ -205,6 +206,8 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
     p.status = status_out;
     p.flags = nullptr;
     p.flag_tiles = 0;
+    p.trace = nullptr;
+    p.debug = env_int("MAS_DP_DEBUG", 0);
     p.order = nullptr;
     p.B = B;
     p.T = T;

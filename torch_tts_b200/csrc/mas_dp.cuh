@@ -54,12 +54,14 @@ struct DpParams {
     int32_t *status;
     uint32_t *flags;        // nullable: [B][flag_tiles] cost-tile-ready flags of the fused kernel (consumed and reset here)
     int flag_tiles;         // mel tiles of 128 rows per utterance
+    unsigned long long *trace;  // nullable diagnostics buffer: [8192 + utterance * 32]: start, tile acquire times, ends
     uint32_t *bits_ws;      // global spill (per CTA region), used when !bits_in_smem
     unsigned char *hop_ws;  // global spill (per CTA region), used when !hop_in_smem
     int B, T, S;
     int R;       // mel rows per chunk = dp_chunk_rows(C)
     int stages;  // cost-tile ring depth (2..kMaxStages)
     int path_dtype;
+    int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads
     int bits_in_smem, hop_in_smem;
     uint32_t off_bits, off_hop, off_stage, stage_bytes, off_bnd_v, off_bnd_o, off_idx, off_end, off_entry, off_bar, off_zero, off_misc;
     unsigned long long bits_words_per_cta, hop_bytes_per_cta;
@@ -321,6 +323,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     if (tid == 0) *nonfinite_s = 0;
     bar_sync(kDpBar, kThreads);  // previous utterance's backtrack is done with the shared buffers
 
+    if (p.trace && tid == 0) p.trace[8192 + (size_t)b * 32 + 0] = globaltimer_ns();
     const int n_chunks = (t_y + R - 1) / R;
     const int n_steps = n_chunks + kDpWarps - 1;
     const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
@@ -344,6 +347,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     uint32_t *f = p.flags + (size_t)b * p.flag_tiles + (row0 >> 7);
                     while (ld_acquire_gpu(f) == 0u) __nanosleep(64);
                     *f = 0u;
+                    if (p.trace) p.trace[8192 + (size_t)b * 32 + 2 + (row0 >> 7)] = globaltimer_ns();
                     fence_proxy_async_all();  // order the bulk (async-proxy) reads below after the acquire
                 }
                 const size_t start = (utt_elem0 + (size_t)row0 * S) * 4;
@@ -363,6 +367,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         *reinterpret_cast<float *>(dst + o) =
                             (o < want) ? *reinterpret_cast<const float *>(src + o) : 0.0f;
                 }
+                if (p.debug & 4) bulk = 0;
                 mbar_arrive_expect_tx(&full[st], bulk);
                 if (bulk) bulk_g2s(dst, src, bulk, &full[st]);
             };
@@ -372,7 +377,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             }
             // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
             // zeroed shared buffer when the plane is 16-byte aligned, plain stores otherwise
-            const size_t pbytes = (pass == 0) ? plane * esize : 0;
+            const size_t pbytes = (pass == 0 && !(p.debug & 1)) ? plane * esize : 0;
             const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
             const size_t quota = align_up((pbytes + n_steps - 1) / n_steps, 512);
             for (int step = 0; step < n_steps; ++step) {
@@ -434,7 +439,8 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
 #define MAS_CHUNK(EDGE, EXACT)                                                                             \
     dp_chunk<C, EDGE, kVec, EXACT>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o, bin_v + slot0, \
                                    bin_o + slot0, bout_v + slot0, bout_o + slot0, x0, lane0, lane31)
-                    if (pass == 0) {
+                    if (p.debug & 2) {
+                    } else if (pass == 0) {
                         if (edge)
                             MAS_CHUNK(true, false);
                         else
@@ -503,6 +509,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     if (!p.bits_in_smem || !p.hop_in_smem) __threadfence_block();
     bar_sync(kDpBar, kThreads);
 
+    if (p.trace && tid == 0) p.trace[8192 + (size_t)b * 32 + 1] = globaltimer_ns();
     // =================== backtrack ===================
     const int y_last = t_y - 1;
     const int J = t_y / kCheck;  // checkpoints stored: after rows 31, 63, ..., 32 J - 1
@@ -548,6 +555,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = (y < t_y) ? (int)idx_s[y] : -1;
     }
     if (p.status && tid == 0) p.status[b] = MAS_UTT_OK;
+    if (p.trace && tid == 0) p.trace[8192 + (size_t)b * 32 + 30] = globaltimer_ns();
     if (p.dur) {
         bar_sync(kDpBar, kThreads);
         for (int x = tid; x < S; x += kThreads) {

@@ -20,14 +20,15 @@ struct FusedParams {
     int n_gemm, n_dp;
 };
 
-template <int C>
-__global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_constant__ FusedParams fp,
-                                                                  const __grid_constant__ CUtensorMap tm_z,
-                                                                  const __grid_constant__ CUtensorMap tm_out)
+template <int C, bool kPair>
+__device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensorMap *tm_z, const CUtensorMap *tm_out,
+                                           unsigned char *smem)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
     if ((int)blockIdx.x < fp.n_gemm) {
-        cost_tc_role<false>(fp.tc, &tm_z, &tm_out, smem, blockIdx.x, fp.n_gemm);
+        if (kPair)
+            cost_tc_role<false, true>(fp.tc, tm_z, tm_out, smem, blockIdx.x >> 1, fp.n_gemm >> 1);
+        else
+            cost_tc_role<false, false>(fp.tc, tm_z, tm_out, smem, blockIdx.x, fp.n_gemm);
     } else {
         if (threadIdx.x >= kThreads) return;
         const int j = (int)blockIdx.x - fp.n_gemm;
@@ -35,6 +36,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_c
         dp_role_init(fp.dp, smem);
         for (int b = j; b < fp.dp.B; b += fp.n_dp) dp_role<C, true>(fp.dp, smem, b, j, g_base);
     }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_constant__ FusedParams fp,
+                                                                  const __grid_constant__ CUtensorMap tm_z,
+                                                                  const __grid_constant__ CUtensorMap tm_out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    fused_body<C, false>(fp, &tm_z, &tm_out, smem);
+}
+
+// contraction CTAs in pairs (clusters of 2, n_gemm even); the DP CTAs ignore their cluster
+template <int C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+    mas_fused_pair_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CUtensorMap tm_z,
+                          const __grid_constant__ CUtensorMap tm_out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    fused_body<C, true>(fp, &tm_z, &tm_out, smem);
 }
 
 static int env_int(const char *name, int dflt)
@@ -78,13 +98,23 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     if (n_dp <= 0) n_dp = B < 64 ? B : 64;
     if (n_dp > B) n_dp = B;
     if (n_dp > sms - 8) n_dp = sms - 8;
+    const bool pair = cost_tc_pair_enabled();
+    const int units = B * (pair ? (m_tiles + 1) / 2 : m_tiles);
     fp.n_dp = n_dp;
     fp.n_gemm = sms - n_dp;
-    const int n_tiles = B * m_tiles;
-    if (fp.n_gemm > n_tiles) fp.n_gemm = n_tiles;
-    fp.tc.wave = n_dp;
+    if (pair) {
+        if (fp.n_gemm > 2 * units) fp.n_gemm = 2 * units;
+        fp.n_gemm &= ~1;
+        if ((fp.n_gemm + fp.n_dp) & 1) fp.n_dp -= 1;  // whole clusters only
+        if (fp.n_dp < 1) return MAS_ERR_UNSUPPORTED_SHAPE;
+    } else if (fp.n_gemm > units) {
+        fp.n_gemm = units;
+    }
+    fp.tc.wave = fp.n_dp;
     fp.tc.flags = flags;
     fp.dp.flags = flags;
+    fp.tc.trace = trace_buffer();
+    fp.dp.trace = fp.tc.trace;
     fp.dp.flag_tiles = m_tiles;
     const size_t smem = dp.smem_bytes > kTcSmem ? dp.smem_bytes : (size_t)kTcSmem;
 
@@ -97,18 +127,22 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = env_int("MAS_FUSED_COOP", 1) ? 1 : 0;
     static thread_local int configured_dev = -1;
     if (dev != configured_dev) {
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         configured_dev = dev;
     }
     cudaError_t e;
     if (dp.C == 1)
-        e = cudaLaunchKernelEx(&cfg, mas_fused_kernel<1>, fp, tc.tm_z, tc.tm_out);
+        e = pair ? cudaLaunchKernelEx(&cfg, mas_fused_pair_kernel<1>, fp, tc.tm_z, tc.tm_out)
+                 : cudaLaunchKernelEx(&cfg, mas_fused_kernel<1>, fp, tc.tm_z, tc.tm_out);
     else if (dp.C == 2)
-        e = cudaLaunchKernelEx(&cfg, mas_fused_kernel<2>, fp, tc.tm_z, tc.tm_out);
+        e = pair ? cudaLaunchKernelEx(&cfg, mas_fused_pair_kernel<2>, fp, tc.tm_z, tc.tm_out)
+                 : cudaLaunchKernelEx(&cfg, mas_fused_kernel<2>, fp, tc.tm_z, tc.tm_out);
     else
         return MAS_ERR_UNSUPPORTED_SHAPE;
     note_launch();
