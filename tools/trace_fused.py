@@ -20,8 +20,8 @@ buf = np.zeros(1 << 16, dtype=np.uint64)
 plan.run(*args); torch.cuda.synchronize()
 rc = L.mas_debug_read_trace(buf.ctypes.data_as(ctypes.c_void_p), buf.size)
 assert rc == 0, rc
-gem = buf[:8192].reshape(128, 64)
-dp = buf[8192:8192 + B * 32].reshape(B, 32).astype(np.int64)
+gem = buf[:148 * 64].reshape(148, 64)
+dp = buf[12288:12288 + B * 32].reshape(B, 32).astype(np.int64)
 t0 = dp[:, 0].min()
 # counts accumulate over the 4 runs: last run's publications are the last (count/4) entries... use modular layout
 cnt = gem[:, 0].astype(np.int64)
@@ -29,7 +29,7 @@ print("gemm ctas with publications:", (cnt > 0).sum(), "counts:", np.unique(cnt)
 rel = lambda x: (x - t0) / 1e3
 NRUN = 4
 rows = []
-for c in range(128):
+for c in range(148):
     k = int(cnt[c]) // NRUN
     if k == 0: continue
     tt = gem[c, 1 + (NRUN - 1) * k: 1 + NRUN * k].astype(np.int64)
@@ -44,3 +44,12 @@ for k in range(8):
     print(f"tile {k} acquired: min {a.min():7.1f} mean {a.mean():7.1f} max {a.max():7.1f}")
 print("forward end: min %.1f mean %.1f max %.1f" % (rel(dp[:, 1]).min(), rel(dp[:, 1]).mean(), rel(dp[:, 1]).max()))
 print("outputs end: min %.1f mean %.1f max %.1f" % (rel(dp[:, 30]).min(), rel(dp[:, 30]).mean(), rel(dp[:, 30]).max()))
+tr = buf[40960:40960 + B * 16].reshape(B, 16).astype(np.int64)
+n_steps = (T + 31) // 32 + 3
+for name, off, labels in [("DP warp 0", 0, ["tile wait", "compute", "bits/hop", "barrier"]),
+                          ("DP warp 3", 4, ["tile wait", "compute", "bits/hop", "barrier"]),
+                          ("producer", 8, ["zero-fill issue", "barrier", "tile issue"])]:
+    tot = tr[:, off:off + len(labels)].sum(1).mean()
+    print(f"{name}: {tot:.0f} cycles in the step loop ({tot / n_steps:.0f} per step)")
+    for j, lab in enumerate(labels):
+        print(f"   {lab:16s} {tr[:, off + j].mean():9.0f} ({tr[:, off + j].mean() / tot:5.1%})")

@@ -147,6 +147,8 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
     p.n_cols = (S + 15) / 16 * 16;
     p.m_tiles = (T + kBM - 1) / kBM;
     p.wave = B;
+    p.seq_k = 1 << 28;
+    p.seq_pure0 = 0;
     p.trace = trace_buffer();
     const char *e = getenv("MAS_TC_DEBUG");
     p.debug = (e && *e) ? atoi(e) : 0;

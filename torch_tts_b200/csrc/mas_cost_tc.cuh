@@ -231,6 +231,7 @@ struct TcParams {
     int n_cols;                    // UMMA N = S rounded up to 16
     int m_tiles;                   // ceil(T / 128)
     int wave;                      // tile order: utterances in groups of `wave`, mel-tile-major inside a group
+    int seq_k, seq_pure0;          // unit schedule: see unit_index() in cost_tc_role (standalone: seq_k huge)
     int z_tma, out_tma;            // tensor maps usable (T % 4 == 0 / S % 4 == 0)
     unsigned long long *trace;     // nullable diagnostics buffer: [cta][64] publication times
     int debug;                     // MAS_TC_DEBUG bit mask (profiling experiments): 1 no A stores, 2 no epilogue stores, 4 no MMA,
@@ -325,6 +326,19 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // n-th work unit of this CTA (pair), or -1 when it has none left.  Rounds 0 .. seq_k-1 stride all
+    // CTAs (pairs); from round seq_k on only the "pure" contraction CTAs (first >= seq_pure0) continue and
+    // share the remaining units among themselves -- the others move on to the DP role (fused kernel).
+    auto unit_index = [&](int n) {
+        int i;
+        if (n < p.seq_k)
+            i = first + n * step;
+        else if (first >= p.seq_pure0)
+            i = p.seq_k * step + (first - p.seq_pure0) + (n - p.seq_k) * (step - p.seq_pure0);
+        else
+            return -1;
+        return i < n_units ? i : -1;
+    };
     // this CTA's mel tile of unit (b, mu), and whether the unit is processed at all
     auto unit_tile = [&](int i, int &b, int &mt) {
         int mu;
@@ -345,7 +359,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         // ======================= B producer =======================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int i = first; i < n_units; i += step) {
+            for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
                 int b, mt;
                 if (!unit_tile(i, b, mt)) continue;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
@@ -368,7 +382,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         // ======================= raw z producer (runs ahead of the operand ring) =======================
         if (lane == 0 && p.z_tma && !(p.debug & 32)) {
             uint32_t it = 0;
-            for (int i = first; i < n_units; i += step) {
+            for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
                 int b, mt;
                 if (!unit_tile(i, b, mt)) continue;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
@@ -384,7 +398,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             // ======================= MMA issuer =======================
             const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kBM : kBM, p.n_cols);
             uint32_t it = 0, nt = 0;
-            for (int i = first; i < n_units; i += step) {
+            for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
                 int b, mt;
                 if (!unit_tile(i, b, mt)) continue;
                 const uint32_t a = nt & 1u, aph = (nt >> 1) & 1u;
@@ -435,7 +449,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         } else if (kPair && lane == 0 && rank == 1) {
             // ======================= forwarder: own B half landed -> rank 0's full barrier =======================
             uint32_t it = 0;
-            for (int i = first; i < n_units; i += step) {
+            for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
                 int b, mt;
                 if (!unit_tile(i, b, mt)) continue;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
@@ -448,7 +462,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     } else if (warp == 2) {
         // ======================= bias: sum of the K-block partials of the unit's utterance =======================
         uint32_t n = 0;
-        for (int i = first; i < n_units; i += step, (void)0) {
+        for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
             int b, mt;
             if (!unit_tile(i, b, mt)) continue;
             const uint32_t buf = n & 1u, ph = (n >> 1) & 1u;
@@ -514,7 +528,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 }
             }
         };
-        for (int i = first; i < n_units; i += step) {
+        for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
             int b, mt;
             if (!unit_tile(i, b, mt)) continue;
             const uint32_t a = nt & 1u, aph = (nt >> 1) & 1u;
@@ -616,7 +630,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         // where this warp announces a converted stage: rank 0's full barriers (a linear window)
         const uint32_t full0 = kPair ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
         long long ph_acc[5] = {0, 0, 0, 0, 0};  // diagnostics: cycles in wait-z, LDS, wait-empty, convert+STS, fence+arrive
-        for (int i = first; i < n_units; i += step) {
+        for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
             int b, mt;
             if (!unit_tile(i, b, mt)) continue;
             const int t = mt * kBM + row;

@@ -13,9 +13,8 @@ static int env_int(const char *name, int dflt)
 // ---------------------------------------------------------------------------
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
-bool dp_plan_try(DpPlan &pl, int T, int S, int C, int stages, bool bits_smem, bool hop_smem)
+bool dp_plan_try(DpPlan &pl, int T, int S, int C, int R, int stages, bool bits_smem, bool hop_smem, size_t budget)
 {
-    const int R = dp_chunk_rows(C);
     const int S_pad = kDpThreads * C;
     const int n_blk = (T + kCheck - 1) / kCheck;  // 32-row blocks of decision words
     const int hop_rows = T / kCheck + 2;
@@ -53,21 +52,24 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int C, int stages, bool bits_smem, bo
     p.hop_bytes_per_cta = (unsigned long long)align_up((size_t)hop_rows * S_pad, 16);
     pl.smem_bytes = off;
     pl.C = C;
-    return off <= (size_t)kSmemBudget;
+    return off <= budget;
 }
 
 // Deepest cost-tile ring that fits next to on-chip decision bits / hops; long utterances spill the
 // bits (then the hops) to the workspace.  stages_hint > 0 forces the ring depth (MAS_DP_STAGES).
-bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint)
+bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R, size_t budget)
 {
     const int C = (S + kDpThreads - 1) / kDpThreads;
     if (C < 1 || C > 8) return false;
+    if (R <= 0) R = dp_chunk_rows(C);
     bool ok = false;
     for (int mode = 0; mode < 3 && !ok; ++mode) {
         const bool bits_smem = (mode == 0), hop_smem = (mode <= 1);
-        const int min_stages = (mode == 2) ? 2 : 3;
+        // the 4 DP warps work on 4 consecutive chunks at once, so the ring needs at least kDpWarps stages
+        // (then without prefetch distance); on-chip bits / hops are only worth it with one stage to spare
+        const int min_stages = (mode == 2) ? kDpWarps : kDpWarps + 1;
         for (int st = (stages_hint > 0 ? stages_hint : 6); st >= min_stages && !ok; --st) {
-            ok = dp_plan_try(pl, T, S, C, st, bits_smem, hop_smem);
+            ok = dp_plan_try(pl, T, S, C, R, st, bits_smem, hop_smem, budget);
             if (stages_hint > 0) break;
         }
     }
@@ -83,8 +85,8 @@ __global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
     extern __shared__ __align__(128) unsigned char smem[];
     const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
     uint32_t g_base = 0;
-    dp_role_init(p, smem);
-    dp_role<C, kVec>(p, smem, b, blockIdx.x, g_base);
+    dp_role_init(p, smem, threadIdx.x, kDpBar);
+    dp_role<C, dp_chunk_rows(C), kVec>(p, smem, b, blockIdx.x, g_base, threadIdx.x, kDpBar);
 }
 
 // ---------------------------------------------------------------------------
@@ -156,7 +158,7 @@ __global__ void mas_expand_kernel(const int32_t *__restrict__ idx, unsigned char
 size_t dp_workspace_bytes(int B, int T, int S)
 {
     DpPlan pl{};
-    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0))) return 0;
+    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), 0, kSmemBudget)) return 0;
     return align_up((size_t)B * 4, 256) + align_up(pl.ws_bits_bytes, 256) + align_up(pl.ws_hop_bytes, 256);
 }
 
@@ -189,10 +191,11 @@ static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
 // of the launch-order array
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
-               size_t workspace_bytes, int B, int T, int S, int32_t **order_out)
+               size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget)
 {
     pl = DpPlan{};
-    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0))) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), R, smem_budget ? smem_budget : (size_t)kSmemBudget))
+        return MAS_ERR_UNSUPPORTED_SHAPE;
     const size_t need = dp_workspace_bytes(B, T, S);
     if (need && (!workspace || workspace_bytes < need)) return MAS_ERR_WORKSPACE;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -206,7 +209,8 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
     p.status = status_out;
     p.flags = nullptr;
     p.flag_tiles = 0;
-    p.trace = nullptr;
+    p.zero_flags = nullptr;
+    p.trace = trace_buffer();
     p.debug = env_int("MAS_DP_DEBUG", 0);
     p.order = nullptr;
     p.B = B;
@@ -228,7 +232,7 @@ int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, v
     DpPlan pl;
     int32_t *order = nullptr;
     int rc = dp_prepare(pl, neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, workspace,
-                        workspace_bytes, B, T, S, &order);
+                        workspace_bytes, B, T, S, &order, 0, 0);
     if (rc) return rc;
     DpParams &p = pl.p;
     // Length bucketing: when the batch is more than one wave of CTAs, launch the

@@ -54,11 +54,13 @@ struct DpParams {
     int32_t *status;
     uint32_t *flags;        // nullable: [B][flag_tiles] cost-tile-ready flags of the fused kernel (consumed and reset here)
     int flag_tiles;         // mel tiles of 128 rows per utterance
-    unsigned long long *trace;  // nullable diagnostics buffer: [8192 + utterance * 32]: start, tile acquire times, ends
+    uint32_t *zero_flags;   // nullable: [B] set by whoever zero-fills the path plane of an utterance (fused kernel: the
+                            // contraction CTAs, once they run out of tiles); consumed and reset here
+    unsigned long long *trace;  // nullable diagnostics buffer: [12288 + utterance * 32]: start, tile acquire times, ends
     uint32_t *bits_ws;      // global spill (per CTA region), used when !bits_in_smem
     unsigned char *hop_ws;  // global spill (per CTA region), used when !hop_in_smem
     int B, T, S;
-    int R;       // mel rows per chunk = dp_chunk_rows(C)
+    int R;       // mel rows per chunk (template parameter of the role; 32, 16 or 8)
     int stages;  // cost-tile ring depth (2..kMaxStages)
     int path_dtype;
     int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads
@@ -218,40 +220,53 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
 }
 
 // one chunk (<= R rows) of this warp's columns; bin/bout point at the ring slot of the chunk's first row
-template <int C, bool kEdge, bool kVec, bool kExact>
+template <int C, int R, bool kEdge, bool kVec, bool kExact>
 __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *tile,
                                          int S, int rows, int row0, float &carry_v, int &carry_o, const float *bin_v,
                                          const int *bin_o, float *bout_v, int *bout_o, int x0, bool lane0, bool lane31)
 {
-    constexpr int R = dp_chunk_rows(C);
     // Threads whose columns lie past S re-read the last real columns instead of whatever
     // follows the row: their results are never used, but they must not invent NaNs.
     // (A thread straddling S reads at most C-1 floats of the next row, or of the zeroed
     // pad the producer keeps behind every tile.)
     const float *trow = tile + (x0 < S ? x0 : S - C);
-    if (rows == R) {
+    // 8 rows per trip: small enough to stay in the instruction cache (a fully unrolled 32-row body is
+    // ~10 KB per variant and its cold fetch cost more than the rows themselves), large enough that the
+    // decision bits are still set with immediates; the 8-bit group is merged into the chunk word per trip.
+    int r = 0;
+#pragma unroll 1
+    for (; r + 8 <= rows; r += 8) {
+        uint32_t w8[C];
 #pragma unroll
-        for (int r = 0; r < R; r += 4)
-            dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, wl, trow + (size_t)r * S, S, r, carry_v, carry_o, bin_v + r,
-                                               bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
-    } else {
-        int r = 0;
-        for (; r + 4 <= rows; r += 4)
-            dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, wl, trow + (size_t)r * S, S, r, carry_v, carry_o, bin_v + r,
-                                               bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
-        for (; r < rows; ++r)
-            dp_rows<C, 1, kEdge, kVec, kExact>(v, org, fin, wl, trow + (size_t)r * S, S, r, carry_v, carry_o, bin_v + r,
-                                               bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
+        for (int k = 0; k < C; ++k) w8[k] = 0u;
+        dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
+                                           bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
+        dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, w8, trow + (size_t)(r + 4) * S, S, 4, carry_v, carry_o,
+                                           bin_v + r + 4, bin_o + r + 4, bout_v + r + 4, bout_o + r + 4, row0 + r + 4, x0,
+                                           lane0, lane31);
+#pragma unroll
+        for (int k = 0; k < C; ++k) wl[k] |= w8[k] << r;
+    }
+#pragma unroll 1
+    for (; r < rows; ++r) {
+        uint32_t w8[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) w8[k] = 0u;
+        dp_rows<C, 1, kEdge, kVec, kExact>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
+                                           bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
+#pragma unroll
+        for (int k = 0; k < C; ++k) wl[k] |= w8[k] << r;
     }
 }
 
 // checkpoint row c_j: c_0 = 0, c_j = 32 j - 1
 __device__ __forceinline__ int check_row(int j) { return j == 0 ? 0 : kCheck * j - 1; }
 
-// one-time per-CTA setup of the DP role (mbarriers, the constant boundary ring, the zero page)
-__device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *smem)
+// one-time setup of a DP team (mbarriers, the constant boundary ring, the zero page).  A team is kThreads
+// consecutive threads (tid = 0..kThreads-1 inside the team) with its own shared-memory region and
+// named barrier `bar`; the standalone kernel runs one team per CTA, the fused kernel up to two.
+__device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *smem, int tid, int bar)
 {
-    const int tid = threadIdx.x;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
     float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);
     int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
@@ -267,20 +282,19 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
     }
     for (int i = tid; i < kZeroBytes / 16; i += kThreads) reinterpret_cast<uint4 *>(zero_s)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();  // zero_s is read by the bulk-store engine
-    bar_sync(kDpBar, kThreads);
+    bar_sync(bar, kThreads);
 }
 
-// Aligns utterance b.  Runs on the first kThreads threads of the CTA; `slot` selects the CTA's region of
+// Aligns utterance b.  Runs on the kThreads threads of one team; `slot` selects the team's region of
 // the spill workspace; g_base is the running cost-tile counter of this CTA's stage ring (mbarrier phases
 // continue across utterances).
-template <int C, bool kVec>
-__device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base)
+template <int C, int R, bool kVec>
+__device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
+                                        int bar)
 {
-    const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int T = p.T, S = p.S;
-    constexpr int R = dp_chunk_rows(C);
     const int t_y = p.t_ys[b], t_x = p.t_xs[b];
     constexpr int S_pad = kDpThreads * C;
     const int esize = path_elem_size(p.path_dtype);
@@ -321,9 +335,9 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     const uint32_t n_stages = (uint32_t)p.stages;
     int *nonfinite_s = reinterpret_cast<int *>(smem + p.off_misc);
     if (tid == 0) *nonfinite_s = 0;
-    bar_sync(kDpBar, kThreads);  // previous utterance's backtrack is done with the shared buffers
+    bar_sync(bar, kThreads);  // previous utterance's backtrack is done with the shared buffers
 
-    if (p.trace && tid == 0) p.trace[8192 + (size_t)b * 32 + 0] = globaltimer_ns();
+    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 0] = globaltimer_ns();
     const int n_chunks = (t_y + R - 1) / R;
     const int n_steps = n_chunks + kDpWarps - 1;
     const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
@@ -347,7 +361,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     uint32_t *f = p.flags + (size_t)b * p.flag_tiles + (row0 >> 7);
                     while (ld_acquire_gpu(f) == 0u) __nanosleep(64);
                     *f = 0u;
-                    if (p.trace) p.trace[8192 + (size_t)b * 32 + 2 + (row0 >> 7)] = globaltimer_ns();
+                    if (p.trace) p.trace[12288 + (size_t)b * 32 + 2 + (row0 >> 7)] = globaltimer_ns();
                     fence_proxy_async_all();  // order the bulk (async-proxy) reads below after the acquire
                 }
                 const size_t start = (utt_elem0 + (size_t)row0 * S) * 4;
@@ -377,10 +391,12 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             }
             // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
             // zeroed shared buffer when the plane is 16-byte aligned, plain stores otherwise
-            const size_t pbytes = (pass == 0 && !(p.debug & 1)) ? plane * esize : 0;
+            const size_t pbytes = (pass == 0 && !(p.debug & 1) && !p.zero_flags) ? plane * esize : 0;
             const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
             const size_t quota = align_up((pbytes + n_steps - 1) / n_steps, 512);
+            long long pacc[3] = {0, 0, 0};  // diagnostics: cycles in zero-fill issue, barrier, tile issue
             for (int step = 0; step < n_steps; ++step) {
+                const long long q0 = p.trace ? clock64() : 0;
                 size_t lo = (size_t)step * quota, hi = lo + quota;
                 if (lo > pbytes) lo = pbytes;
                 if (hi > pbytes || step == n_steps - 1) hi = pbytes;
@@ -395,10 +411,18 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         zero_bytes_warp(path_b + lo, hi - lo, lane);
                     }
                 }
-                bar_sync(kDpBar, kThreads);
+                const long long q1 = p.trace ? clock64() : 0;
+                bar_sync(bar, kThreads);
+                const long long q2 = p.trace ? clock64() : 0;
                 const int freed = step - (kDpWarps - 1);
                 if (lane == 0 && freed >= 0 && freed + (int)n_stages < n_chunks) issue_tile(freed + (int)n_stages);
+                if (p.trace) {
+                    const long long q3 = clock64();
+                    pacc[0] += q1 - q0, pacc[1] += q2 - q1, pacc[2] += q3 - q2;
+                }
             }
+            if (p.trace && lane == 0)
+                for (int j = 0; j < 3; ++j) p.trace[40960 + (size_t)b * 16 + 8 + j] = (unsigned long long)pacc[j];
             if (pass == 0 && bulk_ok && lane == 0) bulk_wait_all();  // zeros land before the ones are scattered
         } else {
             // =================== DP warps ===================
@@ -423,8 +447,10 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             float *bout_v = bnd_v + (size_t)(w + 1) * ring;
             int *bout_o = bnd_o + (size_t)(w + 1) * ring;
             const int edge_rows = (w + 1) * 32 * C;  // rows where a column of this warp is still above the diagonal
+            long long dacc[4] = {0, 0, 0, 0};  // diagnostics: cycles in tile wait, compute, bits/hop, barrier
             for (int step = 0; step < n_steps; ++step) {
                 const int c = step - w;
+                long long d0 = p.trace ? clock64() : 0, d1 = d0, d2 = d0, d3 = d0;
                 if (c >= 0 && c < n_chunks) {
                     const uint32_t g = g0 + c;
                     const uint32_t st = g % n_stages;
@@ -435,9 +461,10 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     const float *tile =
                         reinterpret_cast<const float *>(smem + p.off_stage + (size_t)st * p.stage_bytes + mis);
                     mbar_wait(&full[st], (g / n_stages) & 1u);
+                    if (p.trace) d1 = clock64();
                     const bool edge = row0 < edge_rows;
 #define MAS_CHUNK(EDGE, EXACT)                                                                             \
-    dp_chunk<C, EDGE, kVec, EXACT>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o, bin_v + slot0, \
+    dp_chunk<C, R, EDGE, kVec, EXACT>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o, bin_v + slot0, \
                                    bin_o + slot0, bout_v + slot0, bout_o + slot0, x0, lane0, lane31)
                     if (p.debug & 2) {
                     } else if (pass == 0) {
@@ -452,6 +479,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                             MAS_CHUNK(false, true);
                     }
 #undef MAS_CHUNK
+                    if (p.trace) d2 = clock64() + (long long)(__float_as_int(v[0]) & 0);
                     // decision words: R < 32 accumulates 32 / R chunks per word
                     const int end_row = row0 + rows;
                     const bool word_done = ((end_row & (kCheck - 1)) == 0) || (c == n_chunks - 1);
@@ -492,24 +520,31 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         // the right-hand warp must see the restarted origin of our last column
                         if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
                     }
+                    if (p.trace) d3 = clock64();
                 }
-                bar_sync(kDpBar, kThreads);
+                bar_sync(bar, kThreads);
+                if (p.trace) {
+                    const long long d4 = clock64();
+                    dacc[0] += d1 - d0, dacc[1] += d2 - d1, dacc[2] += d3 - d2, dacc[3] += d4 - d3;
+                }
             }
+            if (p.trace && lane == 0 && (w == 0 || w == 3))
+                for (int j = 0; j < 4; ++j) p.trace[40960 + (size_t)b * 16 + (w ? 4 : 0) + j] = (unsigned long long)dacc[j];
             // origin of the last row relative to its checkpoint -> hop row 0
 #pragma unroll
             for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
             saw_nonfinite = !(fabsf(fin) <= 3.0e38f);  // NaN or Inf
         }
         if (saw_nonfinite) *nonfinite_s = 1;
-        bar_sync(kDpBar, kThreads);
+        bar_sync(bar, kThreads);
         passes = pass + 1;
         if (pass == 1 || *nonfinite_s == 0) break;
     }
     g_base += (uint32_t)passes * n_chunks;
     if (!p.bits_in_smem || !p.hop_in_smem) __threadfence_block();
-    bar_sync(kDpBar, kThreads);
+    bar_sync(bar, kThreads);
 
-    if (p.trace && tid == 0) p.trace[8192 + (size_t)b * 32 + 1] = globaltimer_ns();
+    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 1] = globaltimer_ns();
     // =================== backtrack ===================
     const int y_last = t_y - 1;
     const int J = t_y / kCheck;  // checkpoints stored: after rows 31, 63, ..., 32 J - 1
@@ -524,7 +559,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         }
         idx_s[0] = 0;
     }
-    bar_sync(kDpBar, kThreads);
+    bar_sync(bar, kThreads);
     // level 2: independent walks of <= 32 rows, one per thread
     for (int j = tid; j <= J; j += kThreads) {
         const int y_lo = check_row(j) + 1;
@@ -543,7 +578,13 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         }
     }
     for (int x = tid; x < S_pad; x += kThreads) end_s[x] = -1;
-    bar_sync(kDpBar, kThreads);
+    if (p.zero_flags && tid == 0) {
+        // somebody else zero-fills this utterance's path plane: the ones may only follow the zeros
+        uint32_t *f = p.zero_flags + b;
+        while (ld_acquire_gpu(f) == 0u) __nanosleep(64);
+        *f = 0u;
+    }
+    bar_sync(bar, kThreads);
 
     // =================== outputs ===================
     for (int y = tid; y < t_y; y += kThreads) {
@@ -555,9 +596,9 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = (y < t_y) ? (int)idx_s[y] : -1;
     }
     if (p.status && tid == 0) p.status[b] = MAS_UTT_OK;
-    if (p.trace && tid == 0) p.trace[8192 + (size_t)b * 32 + 30] = globaltimer_ns();
+    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 30] = globaltimer_ns();
     if (p.dur) {
-        bar_sync(kDpBar, kThreads);
+        bar_sync(bar, kThreads);
         for (int x = tid; x < S; x += kThreads) {
             int d = 0;
             if (x < t_x) d = end_s[x] - (x > 0 ? end_s[x - 1] : -1);
@@ -566,10 +607,49 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     }
 }
 
+// Zero-fills the dense path planes of utterances first, first + step, ... and raises their zero flag.
+// Runs on a whole CTA that has nothing else left to do (fused kernel); `zbuf` is kZeroFillBuf bytes of
+// shared memory.  The DP role of the utterance's owner waits for the flag before it scatters the ones.
+constexpr uint32_t kZeroFillBuf = 32768;
+__device__ __forceinline__ void zero_fill_role(const DpParams &p, unsigned char *zbuf, int first, int step)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int i = tid; i < (int)(kZeroFillBuf / 16); i += nthr) reinterpret_cast<uint4 *>(zbuf)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    __syncthreads();
+    const size_t pbytes = (size_t)p.T * p.S * path_elem_size(p.path_dtype);
+    for (int b = first; b < p.B; b += step) {
+        unsigned char *path_b = p.path + (size_t)b * pbytes;
+        const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
+        if (bulk_ok) {
+            if (tid == 0) {
+                for (size_t o = 0; o < pbytes; o += kZeroFillBuf)
+                    bulk_s2g(path_b + o, zbuf, (uint32_t)min((size_t)kZeroFillBuf, pbytes - o));
+                bulk_commit();
+                bulk_wait_all();
+                fence_proxy_async_all();
+            }
+        } else {
+            const int warp = tid >> 5, n_warps = nthr >> 5;
+            const size_t seg = align_up((pbytes + n_warps - 1) / n_warps, 512);
+            size_t lo = (size_t)warp * seg, hi = lo + seg;
+            if (lo > pbytes) lo = pbytes;
+            if (hi > pbytes) hi = pbytes;
+            if (hi > lo) zero_bytes_warp(path_b + lo, hi - lo, tid & 31);
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            st_release_gpu(p.zero_flags + b, 1u);
+        }
+    }
+}
+
 // host side (mas_dp.cu)
 size_t dp_workspace_bytes(int B, int T, int S);
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
-               size_t workspace_bytes, int B, int T, int S, int32_t **order_out);
+               size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget);
 
 }  // namespace mas
