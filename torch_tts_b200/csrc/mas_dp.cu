@@ -13,14 +13,15 @@ static int env_int(const char *name, int dflt)
 // ---------------------------------------------------------------------------
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
-bool dp_plan_try(DpPlan &pl, int T, int S, int C, int R, int stages, bool bits_smem, bool hop_smem, size_t budget)
+bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool bits_smem, bool hop_smem, size_t budget)
 {
-    const int S_pad = kDpThreads * C;
+    const int S_pad = W * 32 * C;
     const int n_blk = (T + kCheck - 1) / kCheck;  // 32-row blocks of decision words
     const int hop_rows = T / kCheck + 2;
     size_t off = 0;
     DpParams &p = pl.p;
     p.R = R;
+    p.W = W;
     p.stages = stages;
     p.off_bar = (uint32_t)off;
     off += 128;
@@ -33,9 +34,9 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int C, int R, int stages, bool bits_s
     p.off_stage = (uint32_t)off;
     off += (size_t)stages * p.stage_bytes;
     p.off_bnd_v = (uint32_t)off;
-    off += (size_t)(kDpWarps + 1) * 2 * R * 4;
+    off += (size_t)(W + 1) * 2 * R * 4;
     p.off_bnd_o = (uint32_t)off;
-    off += (size_t)(kDpWarps + 1) * 2 * R * 4;
+    off += (size_t)(W + 1) * 2 * R * 4;
     p.off_zero = (uint32_t)off;
     off += kZeroBytes;
     p.off_idx = (uint32_t)off;
@@ -57,19 +58,30 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int C, int R, int stages, bool bits_s
 
 // Deepest cost-tile ring that fits next to on-chip decision bits / hops; long utterances spill the
 // bits (then the hops) to the workspace.  stages_hint > 0 forces the ring depth (MAS_DP_STAGES).
+// DP warps per team for S text columns: 2 (C = ceil(S / 64) <= 8 columns per thread) up to S = 512, else 4.
+// MAS_DP_WARPS overrides (2 or 4) where the shape allows it.
+int dp_team_warps(int S)
+{
+    int W = S <= 512 ? 2 : 4;
+    const int e = env_int("MAS_DP_WARPS", 0);
+    if (e == 4 || (e == 2 && S <= 512)) W = e;
+    return W;
+}
+
 bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R, size_t budget)
 {
-    const int C = (S + kDpThreads - 1) / kDpThreads;
+    const int W = dp_team_warps(S);
+    const int C = (S + W * 32 - 1) / (W * 32);
     if (C < 1 || C > 8) return false;
-    if (R <= 0) R = dp_chunk_rows(C);
+    if (R <= 0) R = dp_chunk_rows(S);
     bool ok = false;
     for (int mode = 0; mode < 3 && !ok; ++mode) {
         const bool bits_smem = (mode == 0), hop_smem = (mode <= 1);
-        // the 4 DP warps work on 4 consecutive chunks at once, so the ring needs at least kDpWarps stages
-        // (then without prefetch distance); on-chip bits / hops are only worth it with one stage to spare
-        const int min_stages = (mode == 2) ? kDpWarps : kDpWarps + 1;
+        // the W DP warps work on W consecutive chunks at once, so the ring needs at least W stages (then
+        // without prefetch distance); on-chip bits / hops are only worth it with two stages to spare
+        const int min_stages = (mode == 2) ? W : W + 2;
         for (int st = (stages_hint > 0 ? stages_hint : 6); st >= min_stages && !ok; --st) {
-            ok = dp_plan_try(pl, T, S, C, R, st, bits_smem, hop_smem, budget);
+            ok = dp_plan_try(pl, T, S, W, C, R, st, bits_smem, hop_smem, budget);
             if (stages_hint > 0) break;
         }
     }
@@ -79,14 +91,14 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R, size_
     return true;
 }
 
-template <int C, bool kVec>
-__global__ void __launch_bounds__(kThreads, 1) mas_dp_kernel(const DpParams p)
+template <int C, int R, int W, bool kVec>
+__global__ void __launch_bounds__(dp_threads(W), 1) mas_dp_kernel(const DpParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
     uint32_t g_base = 0;
     dp_role_init(p, smem, threadIdx.x, kDpBar);
-    dp_role<C, dp_chunk_rows(C), kVec>(p, smem, b, blockIdx.x, g_base, threadIdx.x, kDpBar);
+    dp_role<C, R, W, kVec>(p, smem, b, blockIdx.x, g_base, threadIdx.x, kDpBar);
 }
 
 // ---------------------------------------------------------------------------
@@ -162,29 +174,29 @@ size_t dp_workspace_bytes(int B, int T, int S)
     return align_up((size_t)B * 4, 256) + align_up(pl.ws_bits_bytes, 256) + align_up(pl.ws_hop_bytes, 256);
 }
 
-template <int C, bool kVec>
+template <int C, int R, int W, bool kVec>
 static int launch_dp_cv(const DpPlan &pl, cudaStream_t stream)
 {
     static thread_local int configured_dev = -1;
     int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     if (dev != configured_dev) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C, R, W, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kSmemBudget));
         configured_dev = dev;
     }
-    mas_dp_kernel<C, kVec><<<pl.p.B, kThreads, pl.smem_bytes, stream>>>(pl.p);
+    mas_dp_kernel<C, R, W, kVec><<<pl.p.B, dp_threads(W), pl.smem_bytes, stream>>>(pl.p);
     note_launch();
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;
 }
 
-template <int C>
+template <int C, int R, int W>
 static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
 {
     // vector cost loads need every tile row 16-byte aligned in shared memory
     const bool vec = (pl.p.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(pl.p.neg_cent) & 15) == 0);
-    return vec ? launch_dp_cv<C, true>(pl, stream) : launch_dp_cv<C, false>(pl, stream);
+    return vec ? launch_dp_cv<C, R, W, true>(pl, stream) : launch_dp_cv<C, R, W, false>(pl, stream);
 }
 
 // fills pl (shared-memory plan + parameters) without launching; `order_out` receives the workspace slot
@@ -248,16 +260,14 @@ int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, v
     } else {
         p.order = nullptr;
     }
-    switch (pl.C) {
-        case 1: return launch_dp_c<1>(pl, stream);
-        case 2: return launch_dp_c<2>(pl, stream);
-        case 3: return launch_dp_c<3>(pl, stream);
-        case 4: return launch_dp_c<4>(pl, stream);
-        case 5: return launch_dp_c<5>(pl, stream);
-        case 6: return launch_dp_c<6>(pl, stream);
-        case 7: return launch_dp_c<7>(pl, stream);
-        case 8: return launch_dp_c<8>(pl, stream);
-    }
+    // (columns per thread, chunk rows, DP warps): W = 2 covers S <= 512, W = 4 the rest
+#define MAS_DP_CASE(CC, RR, WW) \
+    if (pl.C == CC && p.R == RR && p.W == WW) return launch_dp_c<CC, RR, WW>(pl, stream);
+    MAS_DP_CASE(1, 32, 2) MAS_DP_CASE(2, 32, 2) MAS_DP_CASE(3, 32, 2) MAS_DP_CASE(4, 32, 2)
+    MAS_DP_CASE(5, 16, 2) MAS_DP_CASE(6, 16, 2) MAS_DP_CASE(7, 16, 2) MAS_DP_CASE(8, 16, 2)
+    MAS_DP_CASE(1, 32, 4) MAS_DP_CASE(2, 32, 4) MAS_DP_CASE(3, 16, 4) MAS_DP_CASE(4, 16, 4)
+    MAS_DP_CASE(5, 8, 4) MAS_DP_CASE(6, 8, 4) MAS_DP_CASE(7, 8, 4) MAS_DP_CASE(8, 8, 4)
+#undef MAS_DP_CASE
     return MAS_ERR_UNSUPPORTED_SHAPE;
 }
 

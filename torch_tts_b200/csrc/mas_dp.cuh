@@ -31,17 +31,20 @@
 
 namespace mas {
 
-constexpr int kDpWarps = 4;
-constexpr int kDpThreads = kDpWarps * 32;
-constexpr int kThreads = kDpThreads + 32;  // + producer warp
+// A DP team = W DP warps + 1 producer warp.  W = 2 (4 x more columns per thread than lanes need, i.e.
+// C = ceil(S / 64)) is the default: the C cells of a row are independent of each other, so a wider
+// thread has the instruction-level parallelism to hide the max -> add latency, and only every C-th
+// link of the dependency chain pays for a shuffle.  W = 4 serves S > 512.
+constexpr int kMaxDpWarps = 4;
+__host__ __device__ constexpr int dp_threads(int W) { return (W + 1) * 32; }  // + producer warp
 constexpr int kMaxStages = 8;
 constexpr int kCheck = 32;  // checkpoint interval (rows)
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kDpBar = 3;     // named barrier of the DP role (kThreads threads)
 constexpr int kZeroBytes = 8192;  // zeroed shared buffer the path zero-fill bulk-stores from
 
-// mel rows per chunk (= per TMA tile) for C columns per thread: a stage stays <= 32 KB
-__host__ __device__ constexpr int dp_chunk_rows(int C) { return C <= 2 ? 32 : (C <= 4 ? 16 : 8); }
+// mel rows per chunk (= per TMA tile) for S text columns: a stage stays <= 32 KB
+__host__ __device__ constexpr int dp_chunk_rows(int S) { return S <= 256 ? 32 : (S <= 512 ? 16 : 8); }
 
 struct DpParams {
     const float *neg_cent;
@@ -61,6 +64,7 @@ struct DpParams {
     unsigned char *hop_ws;  // global spill (per CTA region), used when !hop_in_smem
     int B, T, S;
     int R;       // mel rows per chunk (template parameter of the role; 32, 16 or 8)
+    int W;       // DP warps per team (template parameter of the role; 2 or 4)
     int stages;  // cost-tile ring depth (2..kMaxStages)
     int path_dtype;
     int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads
@@ -262,11 +266,13 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
 // checkpoint row c_j: c_0 = 0, c_j = 32 j - 1
 __device__ __forceinline__ int check_row(int j) { return j == 0 ? 0 : kCheck * j - 1; }
 
-// one-time setup of a DP team (mbarriers, the constant boundary ring, the zero page).  A team is kThreads
-// consecutive threads (tid = 0..kThreads-1 inside the team) with its own shared-memory region and
+// one-time setup of a DP team (mbarriers, the constant boundary ring, the zero page).  A team is
+// dp_threads(W) consecutive threads (tid counts inside the team) with its own shared-memory region and
 // named barrier `bar`; the standalone kernel runs one team per CTA, the fused kernel up to two.
 __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *smem, int tid, int bar)
+
 {
+    const int nthr = dp_threads(p.W);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
     float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);
     int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
@@ -276,19 +282,19 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
         fence_mbar_init();
     }
     // ring 0 stands in for "the warp left of warp 0": column -1 is the -1e9 sentinel (core.pyx:24)
-    for (int i = tid; i < 2 * p.R; i += kThreads) {
+    for (int i = tid; i < 2 * p.R; i += nthr) {
         bnd_v[i] = kNeg;
         bnd_o[i] = 0;
     }
-    for (int i = tid; i < kZeroBytes / 16; i += kThreads) reinterpret_cast<uint4 *>(zero_s)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kZeroBytes / 16; i += nthr) reinterpret_cast<uint4 *>(zero_s)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();  // zero_s is read by the bulk-store engine
-    bar_sync(bar, kThreads);
+    bar_sync(bar, nthr);
 }
 
-// Aligns utterance b.  Runs on the kThreads threads of one team; `slot` selects the team's region of
+// Aligns utterance b.  Runs on the dp_threads(W) threads of one team; `slot` selects the team's region of
 // the spill workspace; g_base is the running cost-tile counter of this CTA's stage ring (mbarrier phases
 // continue across utterances).
-template <int C, int R, bool kVec>
+template <int C, int R, int W, bool kVec>
 __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
                                         int bar)
 {
@@ -296,7 +302,9 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     const int lane = tid & 31;
     const int T = p.T, S = p.S;
     const int t_y = p.t_ys[b], t_x = p.t_xs[b];
-    constexpr int S_pad = kDpThreads * C;
+    constexpr int S_pad = W * 32 * C;
+    constexpr int kThreads = dp_threads(W);
+    constexpr int kDpWarps = W;
     const int esize = path_elem_size(p.path_dtype);
     const size_t plane = (size_t)T * S;
     unsigned char *path_b = p.path + (size_t)b * plane * esize;
@@ -647,6 +655,7 @@ __device__ __forceinline__ void zero_fill_role(const DpParams &p, unsigned char 
 }
 
 // host side (mas_dp.cu)
+int dp_team_warps(int S);
 size_t dp_workspace_bytes(int B, int T, int S);
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,

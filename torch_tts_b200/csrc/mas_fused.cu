@@ -18,11 +18,9 @@ struct FusedParams {
     TcParams tc;
     DpParams dp;
     int n_dp;              // the first n_dp CTAs turn into DP CTAs after their share of the contraction
-    int teams;             // DP teams per DP CTA (1 or 2), each with its own shared-memory region
-    uint32_t team_smem;    // bytes between the teams' regions
 };
 
-template <int C, int R, bool kPair>
+template <int C, int R, int W, bool kPair>
 __device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensorMap *tm_z, const CUtensorMap *tm_out,
                                            unsigned char *smem)
 {
@@ -37,36 +35,31 @@ __device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensor
         if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem, (int)blockIdx.x - fp.n_dp, (int)gridDim.x - fp.n_dp);
         return;
     }
-    // DP CTA: `teams` independent teams of kThreads threads, team g = teams * j + team aligns utterances
-    // g, g + teams * n_dp, ...
-    const int team = (int)threadIdx.x / kThreads;
-    if (team >= fp.teams) return;
-    const int tid = (int)threadIdx.x - team * kThreads;
-    const int g = fp.teams * (int)blockIdx.x + team;
-    unsigned char *tsmem = smem + (size_t)team * fp.team_smem;
-    const int bar = kDpBar + team;
+    // DP CTA j aligns utterances j, j + n_dp, ... on its first dp_threads(W) threads
+    if ((int)threadIdx.x >= dp_threads(W)) return;
+    const int j = (int)blockIdx.x;
     uint32_t g_base = 0;
-    dp_role_init(fp.dp, tsmem, tid, bar);
-    for (int b = g; b < fp.dp.B; b += fp.teams * fp.n_dp) dp_role<C, R, true>(fp.dp, tsmem, b, g, g_base, tid, bar);
+    dp_role_init(fp.dp, smem, threadIdx.x, kDpBar);
+    for (int b = j; b < fp.dp.B; b += fp.n_dp) dp_role<C, R, W, true>(fp.dp, smem, b, j, g_base, threadIdx.x, kDpBar);
 }
 
-template <int C, int R>
+template <int C, int R, int W>
 __global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_constant__ FusedParams fp,
                                                                   const __grid_constant__ CUtensorMap tm_z,
                                                                   const __grid_constant__ CUtensorMap tm_out)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    fused_body<C, R, false>(fp, &tm_z, &tm_out, smem);
+    fused_body<C, R, W, false>(fp, &tm_z, &tm_out, smem);
 }
 
 // contraction CTAs in pairs (clusters of 2, n_gemm even); the DP CTAs ignore their cluster
-template <int C, int R>
+template <int C, int R, int W>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     mas_fused_pair_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CUtensorMap tm_z,
                           const __grid_constant__ CUtensorMap tm_out)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    fused_body<C, R, true>(fp, &tm_z, &tm_out, smem);
+    fused_body<C, R, W, true>(fp, &tm_z, &tm_out, smem);
 }
 
 static int env_int(const char *name, int dflt)
@@ -79,7 +72,7 @@ bool fused_supported(int B, int D, int T, int S)
 {
     if (env_int("MAS_NO_FUSED", 0)) return false;
     // tensor-map stores / vector cost loads need 16-byte rows; the contraction takes S <= 256
-    return cost_tc_supported(B, D, T, S) && (S % 4 == 0) && (T % 4 == 0) && S <= 2 * kDpThreads;
+    return cost_tc_supported(B, D, T, S) && (S % 4 == 0) && (T % 4 == 0) && S <= kNMax;
 }
 
 // tile flags [B][m_tiles] followed by the zero-fill flags [B]
@@ -99,33 +92,18 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
                              cost_ws_bytes, B, D, T, S, flags, B * (m_tiles + 1), stream);
     if (rc) return rc;
     if (!tc.p.z_tma || !tc.p.out_tma) return MAS_ERR_UNSUPPORTED_SHAPE;
-    // DP side: two teams per CTA (8-row chunks, half the shared memory each) when everything stays on chip
     DpPlan dp;
-    int teams = env_int("MAS_FUSED_TEAMS", 1);
-    const int C = (S + kDpThreads - 1) / kDpThreads;
-    if (teams == 2) {
-        const size_t half = ((size_t)kSmemBudget / 2) & ~(size_t)1023;
-        rc = dp_prepare(dp, neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes,
-                        B, T, S, nullptr, dp_chunk_rows(C) / 4 < 8 ? 8 : dp_chunk_rows(C) / 4, half);
-        if (rc || !dp.p.bits_in_smem || !dp.p.hop_in_smem || B < 2) teams = 1;
-    }
-    if (teams != 2) {
-        teams = 1;
-        rc = dp_prepare(dp, neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes,
-                        B, T, S, nullptr, 0, 0);
-        if (rc) return rc;
-    }
+    rc = dp_prepare(dp, neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T,
+                    S, nullptr, 0, 0);
+    if (rc) return rc;
     FusedParams fp;
     fp.tc = tc.p;
     fp.dp = dp.p;
-    fp.teams = teams;
-    fp.team_smem = (uint32_t)(((size_t)kSmemBudget / 2) & ~(size_t)1023);
-    // DP CTAs (MAS_FUSED_DP_CTAS overrides): one utterance per team at a time, at most 64 CTAs
+    // DP CTAs (MAS_FUSED_DP_CTAS overrides): one utterance per CTA at a time, at most 64 CTAs
     const bool pair = cost_tc_pair_enabled();
-    const int want = (B + teams - 1) / teams;
     int n_dp = env_int("MAS_FUSED_DP_CTAS", 0);
-    if (n_dp <= 0) n_dp = want < 64 / teams ? want : 64 / teams;
-    if (n_dp > want) n_dp = want;
+    if (n_dp <= 0) n_dp = B < 64 ? B : 64;
+    if (n_dp > B) n_dp = B;
     int grid = sms;
     if (pair) {
         grid &= ~1;
@@ -135,34 +113,35 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     if (n_dp < 1) return MAS_ERR_UNSUPPORTED_SHAPE;
     fp.n_dp = n_dp;
     // Unit schedule: all CTAs take seq_k rounds of units, then the DP CTAs leave.  Pick seq_k with a small
-    // cost model (unit ~7 us, DP ~25 ns per mel row + 5 us): the contraction must not end long after the DP
+    // cost model (unit ~7 us, DP ~40 ns per mel row + 8 us): the contraction must not end long after the DP
     // could, and the DP must not start long before its tiles exist.
     const int per = pair ? 2 : 1;
     const int P = grid / per, P_pure = (grid - n_dp) / per;
     const int units = B * (pair ? (m_tiles + 1) / 2 : m_tiles);
-    const int utts_per_team = (B + n_dp * teams - 1) / (n_dp * teams);
+    const int utts_per_cta = (B + n_dp - 1) / n_dp;
     int best_k = 0;
     double best_t = 1e30;
     for (int k = 0; k <= 8; ++k) {
         const int rest = units - k * P > 0 ? units - k * P : 0;
         const double t_u = 7.0;
         const double gemm_end = (k + (rest + P_pure - 1) / P_pure) * t_u;
-        const double dp_end = k * t_u + utts_per_team * (T * 0.025 + 5.0);
+        const double dp_end = k * t_u + utts_per_cta * (T * 0.040 + 8.0);
         const double t = (gemm_end + 8.0 > dp_end) ? gemm_end + 8.0 : dp_end;
         if (t < best_t - 1e-9) best_t = t, best_k = k;
         if (rest == 0) break;
     }
     fp.tc.seq_k = env_int("MAS_FUSED_ROUNDS", -1) >= 0 ? env_int("MAS_FUSED_ROUNDS", -1) : best_k;
     fp.tc.seq_pure0 = n_dp / per;
-    fp.tc.wave = fp.n_dp * teams;
+    fp.tc.wave = fp.n_dp;
     fp.tc.flags = flags;
     fp.dp.flags = flags;
     fp.tc.trace = trace_buffer();
     fp.dp.trace = fp.tc.trace;
     fp.dp.flag_tiles = m_tiles;
     fp.dp.zero_flags = env_int("MAS_FUSED_ZERO_OFFLOAD", 1) ? flags + (size_t)B * m_tiles : nullptr;
-    size_t smem = teams == 2 ? (size_t)fp.team_smem + dp.smem_bytes : dp.smem_bytes;
+    size_t smem = dp.smem_bytes;
     if (smem < kTcSmem) smem = kTcSmem;
+    if (smem < kZeroFillBuf) smem = kZeroFillBuf;
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -175,23 +154,27 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     cfg.attrs = attr;
     cfg.numAttrs = env_int("MAS_FUSED_COOP", 1) ? 1 : 0;
     cudaError_t e = cudaErrorInvalidValue;
-#define MAS_FUSED_CASE(CC, RR)                                                                                       \
-    if (dp.C == CC && dp.p.R == RR) {                                                                                \
-        static thread_local int cfg_dev = -1;                                                                        \
-        if (dev != cfg_dev) {                                                                                        \
-            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<CC, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                              kSmemBudget));                                                         \
-            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_pair_kernel<CC, RR>,                                         \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));            \
-            cfg_dev = dev;                                                                                           \
-        }                                                                                                            \
-        e = pair ? cudaLaunchKernelEx(&cfg, mas_fused_pair_kernel<CC, RR>, fp, tc.tm_z, tc.tm_out)                   \
-                 : cudaLaunchKernelEx(&cfg, mas_fused_kernel<CC, RR>, fp, tc.tm_z, tc.tm_out);                       \
+#define MAS_FUSED_CASE(CC, WW)                                                                                   \
+    if (dp.C == CC && dp.p.R == 32 && dp.p.W == WW) {                                                            \
+        static thread_local int cfg_dev = -1;                                                                    \
+        if (dev != cfg_dev) {                                                                                    \
+            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<CC, 32, WW>,                                      \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));        \
+            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_pair_kernel<CC, 32, WW>,                                 \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));        \
+            cfg_dev = dev;                                                                                       \
+        }                                                                                                        \
+        e = pair ? cudaLaunchKernelEx(&cfg, mas_fused_pair_kernel<CC, 32, WW>, fp, tc.tm_z, tc.tm_out)           \
+                 : cudaLaunchKernelEx(&cfg, mas_fused_kernel<CC, 32, WW>, fp, tc.tm_z, tc.tm_out);               \
     }
-    MAS_FUSED_CASE(1, 32)
-    else MAS_FUSED_CASE(1, 8)
-    else MAS_FUSED_CASE(2, 32)
-    else MAS_FUSED_CASE(2, 8)
+    // S <= 256 (the contraction's limit): C = ceil(S / 64) columns per thread with 2 DP warps, or
+    // ceil(S / 128) with 4 (MAS_DP_WARPS=4)
+    MAS_FUSED_CASE(1, 2)
+    else MAS_FUSED_CASE(2, 2)
+    else MAS_FUSED_CASE(3, 2)
+    else MAS_FUSED_CASE(4, 2)
+    else MAS_FUSED_CASE(1, 4)
+    else MAS_FUSED_CASE(2, 4)
     else return MAS_ERR_UNSUPPORTED_SHAPE;
 #undef MAS_FUSED_CASE
     note_launch();
