@@ -30,6 +30,7 @@ FUSED_BYTES = 4 * D * T + 2 * 4 * D * S + 4 * T * S        # read z_p, m_p, logs
 MAS_BYTES = 2 * 4 * T * S                                   # read neg_cent, write path
 COST_BYTES = 4 * D * T + 2 * 4 * D * S + 4 * T * S          # read z_p, m_p, logs_p; write neg_cent
 COST_FLOPS = 4 * T * S * D                                  # two K=D contractions
+CPU_BASELINE_REPS = 120                                     # ~10 s of host work at ~90 ms per batch
 
 
 def parse():
@@ -237,60 +238,92 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- per-kernel timing on the same stream (dominant kernel -> roofline)
+    # ---- per-kernel timing on the same stream, each call sequence replayed from a CUDA graph so that
+    #      host launch overhead is not in the number (dominant kernel -> roofline)
     kern = {}
-    nc_buf = torch.empty((B, T, S), dtype=torch.float32, device=dev)
-    reps = max(10, min(args.steps, 30))
-
-    def time_calls(fn):
-        for _ in range(3):
-            fn(0)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(reps):
-            fn(i)
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
-
     st = torch.cuda.current_stream(dev).cuda_stream
     cost_ws = torch.empty(L.mas_neg_cent_workspace_bytes(B, D, T, S), dtype=torch.uint8, device=dev)
     dp_ws = torch.empty(max(L.mas_maximum_path_workspace_bytes(B, T, S), 256), dtype=torch.uint8, device=dev)
     nc_sets = [torch.empty((B, T, S), dtype=torch.float32, device=dev) for _ in range(NSETS)]
 
-    def cost_fn(i):
+    def cost_fn(i, stream):
         k = i % NSETS
         z, m, l, _, _ = dev_sets[k]
-        L.mas_neg_cent_f32(z.data_ptr(), m.data_ptr(), l.data_ptr(), nc_sets[k].data_ptr(), None, cost_ws.data_ptr(),
-                           cost_ws.numel(), B, D, T, S, st)
+        rc = L.mas_neg_cent_f32(z.data_ptr(), m.data_ptr(), l.data_ptr(), nc_sets[k].data_ptr(), None,
+                                cost_ws.data_ptr(), cost_ws.numel(), B, D, T, S, stream)
+        assert rc == 0, rc
 
-    def dp_fn(i):
+    def dp_fn(i, stream):
         k = i % NSETS
         _, _, _, ty, tx = dev_sets[k]
         p = plans[k]
-        L.mas_maximum_path_f32(nc_sets[k].data_ptr(), ty.data_ptr(), tx.data_ptr(), p.path.data_ptr(), 0,
-                               p.dur.data_ptr(), p.idx.data_ptr(), p.status.data_ptr(), dp_ws.data_ptr(),
-                               dp_ws.numel(), B, T, S, st)
+        rc = L.mas_maximum_path_f32(nc_sets[k].data_ptr(), ty.data_ptr(), tx.data_ptr(), p.path.data_ptr(), 0,
+                                    p.dur.data_ptr(), p.idx.data_ptr(), p.status.data_ptr(), dp_ws.data_ptr(),
+                                    dp_ws.numel(), B, T, S, stream)
+        assert rc == 0, rc
 
-    kern["neg_cent_ms"] = time_calls(cost_fn)
-    kern["maximum_path_ms"] = time_calls(dp_fn)
-    del nc_buf
+    def time_graph(fn, env=None):
+        old = {}
+        for k_, v_ in (env or {}).items():
+            old[k_] = os.environ.get(k_)
+            os.environ[k_] = v_
+        try:
+            for i in range(NSETS):
+                fn(i, st)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cs = torch.cuda.current_stream(dev).cuda_stream
+                for i in range(2 * NSETS):
+                    fn(i, cs)
+            g.replay()
+            torch.cuda.synchronize()
+            a_, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            a_.record()
+            for _ in range(reps):
+                g.replay()
+            b2.record()
+            torch.cuda.synchronize()
+            return a_.elapsed_time(b2) / (reps * 2 * NSETS)
+        finally:
+            for k_, v_ in old.items():
+                if v_ is None:
+                    os.environ.pop(k_, None)
+                else:
+                    os.environ[k_] = v_
 
-    # ---- end to end: pinned host buffers -> H2D -> align -> D2H of durations + compact path
+    kern["neg_cent_ms"] = time_graph(cost_fn)                      # prior preparation + contraction, standalone
+    kern["prior_prep_ms"] = time_graph(cost_fn, {"MAS_TC_DEBUG": "8"})   # the prior preparation kernel alone
+    kern["maximum_path_ms"] = time_graph(dp_fn)                    # standalone MAS on a resident cost plane
+    kern["fused_kernel_ms"] = max(ms / args.steps - kern["prior_prep_ms"], 1e-6)   # the step is prior prep + fused kernel
+
+    # ---- end to end through the public call with HOST buffers: pinned host -> H2D (copy stream, double
+    #      buffered) -> align -> D2H of durations + compact path
     out_host = torch.empty((B, S + T), dtype=torch.int32).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
     d2h = out_host.numel() * 4
     stage = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0]) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    main_stream = torch.cuda.current_stream(dev)
 
     def e2e_step(i):
-        hs, ds, p = host_sets[i % NSETS], stage[i % 2], plans[i % NSETS]
-        for h, d_ in zip(hs, ds):
-            d_.copy_(h, non_blocking=True)
+        hs, ds, p, k = host_sets[i % NSETS], stage[i % 2], plans[i % NSETS], i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[k])           # the step that last read this staging set is done
+            for h, d_ in zip(hs, ds):
+                d_.copy_(h, non_blocking=True)
+            ev_ready[k].record(copy_stream)
+        main_stream.wait_event(ev_ready[k])
         p.run(*ds)
         out_host[:, :S].copy_(p.dur, non_blocking=True)
         out_host[:, S:].copy_(p.idx, non_blocking=True)
+        ev_free[k].record(main_stream)
 
+    for k in range(2):
+        ev_free[k].record(main_stream)
     for i in range(3):
         e2e_step(i)
     barrier()
@@ -312,23 +345,26 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, mean, threads = time_cpu(cpu_inputs, reps=20)
+        v, mean, threads = time_cpu(cpu_inputs, reps=CPU_BASELINE_REPS)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": cpu_kind(),
-               "sample": f"20 passes over one full B={B} batch ({mean * 1e3:.1f} ms each): torch CPU neg_cent on "
+               "sample": f"{CPU_BASELINE_REPS} passes over one full B={B} batch ({mean * 1e3:.1f} ms each): torch CPU neg_cent on "
                          f"{threads} threads + serial Cython MAS as shipped; host has {os.cpu_count()} cpus"}
 
     if rank == 0:
         hbm, bf16, how = peaks()
-        if kern["neg_cent_ms"] >= kern["maximum_path_ms"]:
-            t_s = kern["neg_cent_ms"] * 1e-3
-            ach = COST_FLOPS * B / t_s / 1e12
-            roof = {"kernel": "neg_cent contraction", "bound": "tensor", "achieved": ach, "peak": bf16,
-                    "unit": "TFLOP/s", "frac": ach / bf16, "traffic": None, "peak_source": how + " (dense bf16 cuBLAS)"}
-        else:
-            t_s = kern["maximum_path_ms"] * 1e-3
-            ach = MAS_BYTES * B / t_s / 1e9
-            roof = {"kernel": "mas_dp_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                    "frac": ach / hbm, "traffic": None, "peak_source": how}
+        # dominant kernel of the step: the fused contraction + DP kernel.  Algorithmic bytes per launch
+        # (SURVEY 8d): read z_p, m_p, logs_p once, write the dense fp32 path once = 2.228 MB per alignment.
+        t_f = kern["fused_kernel_ms"] * 1e-3
+        ach = FUSED_BYTES * B / t_f / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_fused_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        roof = {"kernel": "mas_fused_pair_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                "frac": ach / hbm, "traffic": traffic, "peak_source": how + " (copy bandwidth, MEASURED_PEAKS.json)",
+                "algorithmic_bytes_per_launch": FUSED_BYTES * B,
+                "tensor": {"achieved": COST_FLOPS * B / t_f / 1e12, "peak": bf16, "unit": "TFLOP/s (algorithmic fp32 "
+                           "flops; the split-bf16 scheme issues 3x as many on the tensor pipe)"}}
         step_s = ms * 1e-3 / args.steps
         fused = {"bound": "hbm", "achieved": FUSED_BYTES * B / step_s / 1e9, "peak": hbm, "unit": "GB/s"}
         fused["frac"] = fused["achieved"] / hbm
