@@ -76,3 +76,89 @@ def test_expand_path_roundtrip(cuda_device):
     again = tts.expand_path(idx, S, torch.float32)
     assert torch.equal(again, path)
     assert torch.equal(tts.expand_path(idx, S, torch.bfloat16).float(), path)
+
+
+@pytest.mark.parametrize("B,S,T", [(70, 64, 256), (9, 192, 384), (5, 100, 260), (3, 32, 132), (4, 256, 1100), (66, 32, 128)])
+def test_fused_shapes_and_many_utterances(cuda_device, B, S, T):
+    """the one-kernel path beyond config 2: more utterances than DP CTAs (a CTA aligns several in turn),
+    C = 1..4 columns per thread, a ragged last mel tile, odd numbers of mel tiles for the CTA pairs."""
+    t_x, t_y = synthetic.ragged_lengths(B, S, T, 5)
+    z_p, m_p, logs_p, x_mask, y_mask = synthetic.prior_inputs(B, S, T, t_x, t_y, seed=11)
+    d = cuda_device
+    attn, w, (idx, dur, status), nc = tts.align(z_p.to(d), m_p.to(d), logs_p.to(d), x_mask.to(d), y_mask.to(d),
+                                                return_compact=True, return_neg_cent=True)
+    assert (status == 0).all()
+    nc_ref = mas_oracle.neg_cent_torch(z_p, m_p, logs_p)
+    assert _rel_err(nc.cpu(), nc_ref) < REL_TOL
+    want = mas_oracle.maximum_path_c(nc.cpu().numpy(), t_y.numpy(), t_x.numpy())
+    assert np.array_equal(attn.squeeze(1).cpu().numpy().astype(np.int32), want)
+    assert torch.equal(dur.sum(1).cpu(), t_y)
+
+
+def test_fused_without_neg_cent_out_skips_dead_tiles(cuda_device):
+    """private cost plane: mel tiles past t_y are never computed; the result is unchanged."""
+    B, S, T = 12, 96, 640
+    t_x, t_y = synthetic.ragged_lengths(B, S, T, 9)
+    t_y = torch.clamp(t_y, max=200)               # most tiles are dead
+    t_x = torch.minimum(t_x, t_y)
+    z_p, m_p, logs_p, x_mask, y_mask = synthetic.prior_inputs(B, S, T, t_x, t_y, seed=2)
+    d = cuda_device
+    a1, w1 = tts.align(z_p.to(d), m_p.to(d), logs_p.to(d), x_mask.to(d), y_mask.to(d))
+    a2, w2, nc = tts.align(z_p.to(d), m_p.to(d), logs_p.to(d), x_mask.to(d), y_mask.to(d), return_neg_cent=True)
+    assert torch.equal(a1, a2) and torch.equal(w1, w2)
+    want = mas_oracle.maximum_path_c(nc.cpu().numpy(), t_y.numpy(), t_x.numpy())
+    assert np.array_equal(a1.squeeze(1).cpu().numpy().astype(np.int32), want)
+
+
+def test_align_plan_graph_replay_is_repeatable(cuda_device):
+    """AlignPlan: one C call per step, CUDA-graph capturable; the tile flags clean up after themselves,
+    so replays (and a change of inputs between replays) give the right answer every time."""
+    B, S, T, D = 8, 128, 512, 192
+    d = cuda_device
+    plan = tts.AlignPlan(B, D, T, S, d)
+    outs = []
+    bufs = None
+    for seed in (1, 2, 1):
+        t_x, t_y = synthetic.ragged_lengths(B, S, T, seed)
+        z_p, m_p, logs_p, _, _ = synthetic.prior_inputs(B, S, T, t_x, t_y, seed=seed)
+        new = (z_p.to(d), m_p.to(d), logs_p.to(d), t_y.to(d), t_x.to(d))
+        if bufs is None:
+            bufs = new
+            plan.capture(0, *bufs)
+        else:
+            for dst, src in zip(bufs, new):
+                dst.copy_(src)
+        for _ in range(3):
+            plan.replay(0)
+        torch.cuda.synchronize()
+        outs.append((plan.idx.clone(), plan.dur.clone()))
+        nc_ref = mas_oracle.neg_cent_torch(z_p, m_p, logs_p)
+        ref = mas_oracle.maximum_path_c(nc_ref.numpy(), t_y.numpy(), t_x.numpy())
+        agree = (plan.path.cpu().numpy().astype(np.int32) == ref).mean()
+        assert agree >= MIN_AGREE
+        assert torch.equal(plan.dur.sum(1).cpu(), t_y)
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+
+
+def test_sharded_align_single_rank_nccl(cuda_device):
+    """align_sharded + compact all-gather over NCCL with a world of one rank (the multi-rank host logic is
+    covered on CPU by tests/test_sharded_cpu.py; tools/run_sharded_check.py checks 2+ GPUs under torchrun)."""
+    import os
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        pytest.skip("a process group already exists")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29731")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda_device)
+    try:
+        B, S, T = 6, 64, 256
+        t_x, t_y = synthetic.ragged_lengths(B, S, T, 3)
+        z_p, m_p, logs_p, x_mask, y_mask = synthetic.prior_inputs(B, S, T, t_x, t_y, seed=3)
+        d = cuda_device
+        attn, w, g_idx, g_dur = tts.align_sharded(z_p.to(d), m_p.to(d), logs_p.to(d), x_mask.to(d), y_mask.to(d),
+                                                  gather=True)
+        assert torch.equal(tts.expand_path(g_idx, S), attn.squeeze(1))
+        assert torch.equal(g_dur.sum(1).cpu(), t_y)
+    finally:
+        dist.destroy_process_group()
