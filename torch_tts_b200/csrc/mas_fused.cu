@@ -99,37 +99,52 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     FusedParams fp;
     fp.tc = tc.p;
     fp.dp = dp.p;
-    // DP CTAs (MAS_FUSED_DP_CTAS overrides): one utterance per CTA at a time, at most 64 CTAs
+    // DP CTAs (MAS_FUSED_DP_CTAS overrides): one per utterance; when the batch is larger than the GPU, nearly
+    // every CTA becomes a DP CTA after the contraction and aligns several utterances in turn (the standalone
+    // MAS kernel reaches the HBM roofline that way: the DP wants every SM's memory pipe)
     const bool pair = cost_tc_pair_enabled();
-    int n_dp = env_int("MAS_FUSED_DP_CTAS", 0);
-    if (n_dp <= 0) n_dp = B < 64 ? B : 64;
-    if (n_dp > B) n_dp = B;
-    int grid = sms;
-    if (pair) {
-        grid &= ~1;
-        n_dp = (n_dp + 1) & ~1;  // whole pairs
+    const int grid = pair ? (sms & ~1) : sms;
+    const int per = pair ? 2 : 1;
+    const int units = B * (pair ? (m_tiles + 1) / 2 : m_tiles);
+    // Unit schedule: all CTAs take seq_k rounds of units, then the DP CTAs leave.  A small cost model (unit
+    // ~7 us, DP ~40 ns per mel row + 8 us per utterance) picks seq_k and, for batches larger than 64, between
+    // 64 DP CTAs and nearly all of them: the contraction must not end long after the DP could, and the DP
+    // must not start long before its tiles exist.
+    auto model = [&](int n_dp_try, int &k_out) {
+        const int P = grid / per, P_pure = (grid - n_dp_try) / per;
+        const int utts = (B + n_dp_try - 1) / n_dp_try;
+        double best = 1e30;
+        for (int k = 0; k <= 64; ++k) {
+            const int rest = units - k * P > 0 ? units - k * P : 0;
+            const double t_u = 7.0;
+            const double gemm_end = (k + (rest + P_pure - 1) / P_pure) * t_u;
+            const double dp_end = k * t_u + utts * (T * 0.040 + 8.0);
+            const double t = (gemm_end + 8.0 > dp_end) ? gemm_end + 8.0 : dp_end;
+            if (t < best - 1e-9) best = t, k_out = k;
+            if (rest == 0) break;
+        }
+        return best;
+    };
+    auto legal = [&](int n) {
+        if (n > B) n = B;
+        if (pair) n = (n + 1) & ~1;  // whole pairs
+        if (n > grid - 8) n = (grid - 8) & ~1;
+        return n;
+    };
+    int n_dp = env_int("MAS_FUSED_DP_CTAS", 0), best_k = 0;
+    if (n_dp > 0) {
+        n_dp = legal(n_dp);
+        model(n_dp, best_k);
+    } else {
+        int k_a = 0, k_b = 0;
+        const int n_a = legal(B < 64 ? B : 64), n_b = legal(B);
+        const double t_a = model(n_a, k_a), t_b = model(n_b, k_b);
+        n_dp = (t_b < t_a) ? n_b : n_a;
+        best_k = (t_b < t_a) ? k_b : k_a;
     }
-    if (n_dp > grid - 8) n_dp = (grid - 8) & ~1;
     if (n_dp < 1) return MAS_ERR_UNSUPPORTED_SHAPE;
     fp.n_dp = n_dp;
-    // Unit schedule: all CTAs take seq_k rounds of units, then the DP CTAs leave.  Pick seq_k with a small
-    // cost model (unit ~7 us, DP ~40 ns per mel row + 8 us): the contraction must not end long after the DP
-    // could, and the DP must not start long before its tiles exist.
-    const int per = pair ? 2 : 1;
-    const int P = grid / per, P_pure = (grid - n_dp) / per;
-    const int units = B * (pair ? (m_tiles + 1) / 2 : m_tiles);
     const int utts_per_cta = (B + n_dp - 1) / n_dp;
-    int best_k = 0;
-    double best_t = 1e30;
-    for (int k = 0; k <= 8; ++k) {
-        const int rest = units - k * P > 0 ? units - k * P : 0;
-        const double t_u = 7.0;
-        const double gemm_end = (k + (rest + P_pure - 1) / P_pure) * t_u;
-        const double dp_end = k * t_u + utts_per_cta * (T * 0.040 + 8.0);
-        const double t = (gemm_end + 8.0 > dp_end) ? gemm_end + 8.0 : dp_end;
-        if (t < best_t - 1e-9) best_t = t, best_k = k;
-        if (rest == 0) break;
-    }
     fp.tc.seq_k = env_int("MAS_FUSED_ROUNDS", -1) >= 0 ? env_int("MAS_FUSED_ROUNDS", -1) : best_k;
     fp.tc.seq_pure0 = n_dp / per;
     fp.tc.wave = fp.n_dp;
@@ -138,7 +153,9 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     fp.tc.trace = trace_buffer();
     fp.dp.trace = fp.tc.trace;
     fp.dp.flag_tiles = m_tiles;
-    fp.dp.zero_flags = env_int("MAS_FUSED_ZERO_OFFLOAD", 1) ? flags + (size_t)B * m_tiles : nullptr;
+    // the contraction-only CTAs zero-fill the path planes when there are enough of them to do it in time
+    const bool offload = env_int("MAS_FUSED_ZERO_OFFLOAD", 1) && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1;
+    fp.dp.zero_flags = offload ? flags + (size_t)B * m_tiles : nullptr;
     size_t smem = dp.smem_bytes;
     if (smem < kTcSmem) smem = kTcSmem;
     if (smem < kZeroFillBuf) smem = kZeroFillBuf;
