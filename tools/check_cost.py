@@ -6,7 +6,8 @@ import torch_tts_b200 as tts
 from oracle import mas_oracle
 from torch_tts_b200 import synthetic, _lib
 dev = torch.device("cuda:0")
-shapes = [(2, 64, 256, False), (3, 80, 300, True), (4, 256, 1024, False), (2, 200, 800, True), (2, 17, 50, False)]
+shapes = [(2, 64, 256, False), (3, 80, 300, True), (4, 256, 1024, False), (2, 200, 800, True), (2, 17, 50, False),
+          (2, 600, 1000, False), (3, 300, 700, True), (1, 1024, 1030, False)]
 if len(sys.argv) > 1 and sys.argv[1] == "big":
     shapes = [(64, 256, 1024, False)]
 for B, S, T, ragged in shapes:

@@ -22,11 +22,12 @@ __global__ void __launch_bounds__(kNMax) mas_prior_images_kernel(const float *__
                                                                 float *__restrict__ bias_part, int D, int S, int n_kb,
                                                                 uint32_t *flags_to_clear, int n_flags)
 {
-    const int kb = blockIdx.x, b = blockIdx.y;
-    const int s = threadIdx.x;
+    const int kb = blockIdx.x, b = blockIdx.y, nb = blockIdx.z;   // K block, utterance, column block
+    const int s_img = threadIdx.x;                                // row of the image
+    const int s = nb * kNMax + s_img;                             // text column
     if (flags_to_clear) {
-        const int n_cta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
-        for (int i = cta * kNMax + s; i < n_flags; i += n_cta * kNMax) flags_to_clear[i] = 0u;
+        const int n_cta = gridDim.x * gridDim.y * gridDim.z, cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        for (int i = cta * kNMax + s_img; i < n_flags; i += n_cta * kNMax) flags_to_clear[i] = 0u;
     }
     const bool live = s < S;
     const size_t base = (size_t)b * D * S + (live ? s : 0);
@@ -51,8 +52,8 @@ __global__ void __launch_bounds__(kNMax) mas_prior_images_kernel(const float *__
         acc4 += -0.5f * (m[j] * m[j]) * rr;                // :1236-1238 (0 when !ok)
         m[j] = m[j] * rr;                                  // m r, :1234
     }
-    unsigned char *img_hi = images + ((size_t)(b * n_kb + kb) * 2 + 0) * kBPart;
-    unsigned char *img_lo = images + ((size_t)(b * n_kb + kb) * 2 + 1) * kBPart;
+    unsigned char *img_hi = images + (((size_t)(b * gridDim.z + nb) * n_kb + kb) * 2 + 0) * kBPart;
+    unsigned char *img_lo = images + (((size_t)(b * gridDim.z + nb) * n_kb + kb) * 2 + 1) * kBPart;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {      // 0: r, 1: m r
 #pragma unroll
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kNMax) mas_prior_images_kernel(const float *__
                 const int k = c * 8 + j * 2;
                 split2(half ? m[k] : r[k], half ? m[k + 1] : r[k + 1], hi[j], lo[j]);
             }
-            const uint32_t off = sw64_offset(s, half * 16 + c * 8);
+            const uint32_t off = sw64_offset(s_img, half * 16 + c * 8);
             *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
@@ -104,14 +105,14 @@ bool cost_tc_supported(int B, int D, int T, int S)
 {
     (void)B;
     (void)T;
-    return S <= kNMax && D >= 1;
+    return S <= 4 * kNMax && D >= 1;
 }
 
 size_t cost_tc_workspace_bytes(int B, int D, int T, int S)
 {
     (void)T;
-    const int n_kb = (D + kDPerKb - 1) / kDPerKb;
-    return align_up((size_t)B * n_kb * 2 * kBPart, 256) + align_up((size_t)B * n_kb * S * 4, 256);
+    const int n_kb = (D + kDPerKb - 1) / kDPerKb, n_blocks = (S + kNMax - 1) / kNMax;
+    return align_up((size_t)B * n_blocks * n_kb * 2 * kBPart, 256) + align_up((size_t)B * n_kb * S * 4, 256);
 }
 
 int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out,
@@ -119,13 +120,13 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
                     int S, uint32_t *flags_to_clear, int n_flags, cudaStream_t stream)
 {
     if (!workspace || workspace_bytes < cost_tc_workspace_bytes(B, D, T, S)) return MAS_ERR_WORKSPACE;
-    const int n_kb = (D + kDPerKb - 1) / kDPerKb;
+    const int n_kb = (D + kDPerKb - 1) / kDPerKb, n_blocks = (S + kNMax - 1) / kNMax;
     unsigned char *images = static_cast<unsigned char *>(workspace);
-    float *bias = reinterpret_cast<float *>(images + align_up((size_t)B * n_kb * 2 * kBPart, 256));
+    float *bias = reinterpret_cast<float *>(images + align_up((size_t)B * n_blocks * n_kb * 2 * kBPart, 256));
     if (stats_out) MAS_CUDA_TRY(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double), stream));
     const char *dbg = getenv("MAS_TC_DEBUG");  // bit 16: reuse the images already in the workspace (timing experiments)
     if (!(dbg && *dbg && (atoi(dbg) & 16))) {
-        mas_prior_images_kernel<<<dim3(n_kb, B), kNMax, 0, stream>>>(m_p, logs_p, images, bias, D, S, n_kb,
+        mas_prior_images_kernel<<<dim3(n_kb, B, n_blocks), kNMax, 0, stream>>>(m_p, logs_p, images, bias, D, S, n_kb,
                                                                      flags_to_clear, n_flags);
         note_launch();
         MAS_CUDA_TRY(cudaGetLastError());
@@ -144,7 +145,7 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
     p.T = T;
     p.S = S;
     p.n_kb = n_kb;
-    p.n_cols = (S + 15) / 16 * 16;
+    p.n_blocks = n_blocks;
     p.m_tiles = (T + kBM - 1) / kBM;
     p.wave = B;
     p.seq_k = 1 << 28;
@@ -189,14 +190,14 @@ int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, floa
     if (g && *g && atoi(g) > 0 && atoi(g) < sms) sms = atoi(g);
     if (plan.p.debug & 8) return MAS_OK;  // timing experiments: prior preparation only
     if (cost_tc_pair_enabled()) {
-        const int n_units = B * ((plan.p.m_tiles + 1) / 2);
+        const int n_units = B * ((plan.p.m_tiles + 1) / 2) * plan.p.n_blocks;
         int grid = 2 * n_units < sms ? 2 * n_units : (sms & ~1);
         if (stats_out)
             mas_cost_tc_pair_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
         else
             mas_cost_tc_pair_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
     } else {
-        const int n_tiles = B * plan.p.m_tiles;
+        const int n_tiles = B * plan.p.m_tiles * plan.p.n_blocks;
         const int grid = n_tiles < sms ? n_tiles : sms;
         if (stats_out)
             mas_cost_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);

@@ -220,7 +220,7 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
 
 struct TcParams {
     const float *z_p;
-    const unsigned char *images;   // [B][n_kb][2 parts][kBPart]
+    const unsigned char *images;   // [B][n_blocks][n_kb][2 parts][kBPart]
     const float *bias_part;        // [B][n_kb][S]
     float *out;                    // [B][T][S]
     double *stats;                 // nullable
@@ -228,7 +228,7 @@ struct TcParams {
     uint32_t *flags;               // nullable: [B][m_tiles], set to 1 (release) when a tile is in memory
     int B, D, T, S;
     int n_kb;                      // K blocks = ceil(D / 16)
-    int n_cols;                    // UMMA N = S rounded up to 16
+    int n_blocks;                  // column blocks of kNMax text columns per utterance (1 for S <= 256)
     int m_tiles;                   // ceil(T / 128)
     int wave;                      // tile order: utterances in groups of `wave`, mel-tile-major inside a group
     int seq_k, seq_pure0;          // unit schedule: see unit_index() in cost_tc_role (standalone: seq_k huge)
@@ -291,7 +291,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     const int lane = tid & 31;
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const int m_units = kPair ? (p.m_tiles + 1) / 2 : p.m_tiles;
-    const int n_units = p.B * m_units;
+    const int n_units = p.B * m_units * p.n_blocks;
 
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -340,33 +340,39 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         return i < n_units ? i : -1;
     };
     // this CTA's mel tile of unit (b, mu), and whether the unit is processed at all
-    auto unit_tile = [&](int i, int &b, int &mt) {
+    // (a unit is one column block nb of one mel tile / tile pair; S <= 256 has a single block)
+    auto unit_tile = [&](int i, int &b, int &mt, int &nb) {
         int mu;
-        tc_unit_coords(p, m_units, i, b, mu);
+        nb = i % p.n_blocks;
+        tc_unit_coords(p, m_units, i / p.n_blocks, b, mu);
         mt = kPair ? 2 * mu + (int)rank : mu;
         return tc_tile_live(p, b, kPair ? 2 * mu : mu);
+    };
+    // text columns of block nb, rounded up to the UMMA N granularity
+    auto block_cols = [&](int nb) {
+        const int left = p.S - nb * kNMax;
+        return ((left < kNMax ? left : kNMax) + 15) & ~15;
     };
     // diagnostics: trace[16384 + cta * 64 + role * 16 + 2 * unit + {0: begin, 1: end}], roles 0 MMA, 1 epilogue, 2 converter, 3 z
     auto tr_mark = [&](int role, uint32_t unit, int which) {
         if (p.trace && unit < 8) p.trace[16384 + (size_t)blockIdx.x * 64 + role * 16 + 2 * unit + which] = globaltimer_ns();
     };
-    // rows of a B image this CTA stages, and their bytes
-    const uint32_t b_rows = kPair ? (uint32_t)p.n_cols / 2 : (uint32_t)p.n_cols;
-    const uint32_t b_bytes = b_rows * kRowBytes;
-    const uint32_t b_off = kPair ? rank * b_bytes : 0u;
 
     if (warp == 0) {
         // ======================= B producer =======================
         if (lane == 0) {
             uint32_t it = 0;
             for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
-                int b, mt;
-                if (!unit_tile(i, b, mt)) continue;
+                int b, mt, nb;
+                if (!unit_tile(i, b, mt, nb)) continue;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
                     unsigned char *stage = smem + s * Cfg::kStage;
-                    const unsigned char *img = p.images + (size_t)(b * p.n_kb + kb) * 2 * kBPart + b_off;
+                    // rows of the B image this CTA stages (a pair: half each), and their bytes
+                    const uint32_t b_bytes = (uint32_t)block_cols(nb) / (kPair ? 2u : 1u) * kRowBytes;
+                    const unsigned char *img = p.images + ((size_t)(b * p.n_blocks + nb) * p.n_kb + kb) * 2 * kBPart +
+                                               (kPair ? rank * b_bytes : 0u);
                     uint64_t *bar = (kPair && rank) ? &bfull[s] : &full[s];
                     if (p.debug & 64) {  // experiment: no B traffic
                         mbar_arrive(bar);
@@ -383,8 +389,8 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         if (lane == 0 && p.z_tma && !(p.debug & 32)) {
             uint32_t it = 0;
             for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
-                int b, mt;
-                if (!unit_tile(i, b, mt)) continue;
+                int b, mt, nb;
+                if (!unit_tile(i, b, mt, nb)) continue;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
                     const uint32_t zs = it % kZStages, zph = (it / kZStages) & 1u;
                     mbar_wait(&zempty[zs], zph ^ 1u);
@@ -396,11 +402,10 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             // ======================= MMA issuer =======================
-            const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kBM : kBM, p.n_cols);
             uint32_t it = 0, nt = 0;
             for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
-                int b, mt;
-                if (!unit_tile(i, b, mt)) continue;
+                int b, mt, nb;
+                if (!unit_tile(i, b, mt, nb)) continue;
                 const uint32_t a = nt & 1u, aph = (nt >> 1) & 1u;
                 if (kPair)
                     mbar_wait_cluster(&acc_empty[a], aph ^ 1u);
@@ -408,6 +413,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     mbar_wait(&acc_empty[a], aph ^ 1u);
                 tc_fence_after();
                 tr_mark(0, nt, 0);
+                const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kBM : kBM, block_cols(nb));
                 const uint32_t tmem_d = tmem_base + a * kNMax;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
@@ -450,8 +456,8 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             // ======================= forwarder: own B half landed -> rank 0's full barrier =======================
             uint32_t it = 0;
             for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
-                int b, mt;
-                if (!unit_tile(i, b, mt)) continue;
+                int b, mt, nb;
+                if (!unit_tile(i, b, mt, nb)) continue;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                     mbar_wait(&bfull[s], ph);
@@ -463,16 +469,17 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         // ======================= bias: sum of the K-block partials of the unit's utterance =======================
         uint32_t n = 0;
         for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
-            int b, mt;
-            if (!unit_tile(i, b, mt)) continue;
+            int b, mt, nb;
+            if (!unit_tile(i, b, mt, nb)) continue;
             const uint32_t buf = n & 1u, ph = (n >> 1) & 1u;
             mbar_wait(&bias_empty[buf], ph ^ 1u);
-            const float *bp = p.bias_part + (size_t)b * p.n_kb * p.S;
+            const float *bp = p.bias_part + (size_t)b * p.n_kb * p.S + nb * kNMax;
+            const int ncols = block_cols(nb), s_left = p.S - nb * kNMax;
             if ((p.S & 3) == 0) {
                 // 4 columns per lane and pass, up to 12 partials in flight per lane; summed in K-block order
-                for (int s = 4 * lane; s < p.n_cols; s += 128) {
+                for (int s = 4 * lane; s < ncols; s += 128) {
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (s < p.S) {
+                    if (s < s_left) {
                         for (int kb0 = 0; kb0 < p.n_kb; kb0 += 12) {
                             float4 part[12];
 #pragma unroll
@@ -489,9 +496,9 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     *reinterpret_cast<float4 *>(bias_s + buf * kNMax + s) = acc;
                 }
             } else {
-                for (int s = lane; s < p.n_cols; s += 32) {
+                for (int s = lane; s < ncols; s += 32) {
                     float acc = 0.f;
-                    if (s < p.S)
+                    if (s < s_left)
                         for (int kb = 0; kb < p.n_kb; ++kb) acc += bp[(size_t)kb * p.S + s];
                     bias_s[buf * kNMax + s] = acc;
                 }
@@ -529,8 +536,8 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             }
         };
         for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
-            int b, mt;
-            if (!unit_tile(i, b, mt)) continue;
+            int b, mt, nb;
+            if (!unit_tile(i, b, mt, nb)) continue;
             const uint32_t a = nt & 1u, aph = (nt >> 1) & 1u;
             mbar_wait(&bias_full[a], aph);
             const float *bias_u = bias_s + a * kNMax;
@@ -538,9 +545,10 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             tc_fence_after();
             if (tid == 128) tr_mark(1, nt, 0);
             const int t = mt * kBM + row;
-            float *orow = p.out + ((size_t)b * p.T + t) * p.S;
+            const int c_base = nb * kNMax, ncols = block_cols(nb), s_left = p.S - c_base;
+            float *orow = p.out + ((size_t)b * p.T + t) * p.S + c_base;
             const uint32_t taddr = tmem_base + a * kNMax + ((uint32_t)(wq * 32) << 16);
-            for (int c0 = 0; c0 < p.n_cols; c0 += 32) {
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c0, r);
                 tmem_ld_wait();
@@ -551,7 +559,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     if (t < p.T) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (c0 + j < p.S) {
+                            if (c0 + j < s_left) {
                                 ssum += (double)v[j];
                                 ssq += (double)v[j] * (double)v[j];
                             }
@@ -569,7 +577,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_3d(tm_out, c0, mt * kBM + wq * 32, b, buf);  // rows >= T / cols >= S are clipped
+                        tma_store_3d(tm_out, c_base + c0, mt * kBM + wq * 32, b, buf);  // rows >= T / cols >= S are clipped
                         bulk_commit();
                         if (c0 == 0 && pend_flag) {
                             bulk_wait_group<1>();  // everything older than the store just committed has landed
@@ -581,7 +589,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 } else if (t < p.T) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c0 + j < p.S) orow[c0 + j] = v[j];
+                        if (c0 + j < s_left) orow[c0 + j] = v[j];
                 }
             }
             tc_fence_before();
@@ -631,8 +639,8 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         const uint32_t full0 = kPair ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
         long long ph_acc[5] = {0, 0, 0, 0, 0};  // diagnostics: cycles in wait-z, LDS, wait-empty, convert+STS, fence+arrive
         for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
-            int b, mt;
-            if (!unit_tile(i, b, mt)) continue;
+            int b, mt, nb;
+            if (!unit_tile(i, b, mt, nb)) continue;
             const int t = mt * kBM + row;
             const bool live = t < p.T && mt < p.m_tiles;
             const float *zb = p.z_p + (size_t)b * p.D * p.T + (live ? t : 0);
