@@ -162,3 +162,24 @@ def test_sharded_align_single_rank_nccl(cuda_device):
         assert torch.equal(g_dur.sum(1).cpu(), t_y)
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,S,T,ragged", [(6, 80, 320, True), (4, 256, 1024, False), (9, 200, 800, True), (3, 600, 1200, False)])
+@pytest.mark.parametrize("scale", [0.01, 0])
+def test_noise_applied_inside_the_dp(cuda_device, B, S, T, ragged, scale):
+    """without a neg_cent_out request the noised cost is never materialised: the DP adds (std * noise) * scale
+    while the cost streams in.  Same path as the route through the explicit noise pass, bit for bit."""
+    t_x, t_y = synthetic.ragged_lengths(B, S, T, 2) if ragged else synthetic.full_lengths(B, S, T)
+    z_p, m_p, logs_p, x_mask, y_mask = synthetic.prior_inputs(B, S, T, t_x, t_y, seed=13)
+    noise = torch.randn((B, T, S), generator=torch.Generator().manual_seed(6))
+    d = cuda_device
+    args = (z_p.to(d), m_p.to(d), logs_p.to(d), x_mask.to(d), y_mask.to(d), scale, noise.to(d))
+    attn_a, w_a, (idx_a, dur_a, st_a) = tts.align(*args, return_compact=True)                  # noise inside the DP
+    attn_b, w_b, (idx_b, dur_b, st_b), nc = tts.align(*args, return_compact=True, return_neg_cent=True)   # explicit pass
+    assert (st_a == 0).all() and (st_b == 0).all()
+    assert torch.equal(idx_a, idx_b) and torch.equal(dur_a, dur_b) and torch.equal(attn_a, attn_b)
+    # and it is the reference's alignment of the reference's noised cost
+    attn_ref, w_ref, nc_ref = mas_oracle.align_torch(z_p, m_p, logs_p, x_mask, y_mask, scale, noise)
+    assert _rel_err(nc.cpu(), nc_ref) < REL_TOL
+    assert (attn_a.cpu() == attn_ref).float().mean().item() >= MIN_AGREE
+    assert torch.equal(w_a.sum((1, 2)).cpu(), w_ref.sum((1, 2)))

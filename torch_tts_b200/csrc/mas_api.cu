@@ -38,7 +38,9 @@ int note_cuda_error(cudaError_t e, const char *what)
 size_t dp_workspace_bytes(int B, int T, int S);
 int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
               int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace, size_t workspace_bytes, int B,
-              int T, int S, cudaStream_t stream);
+              int T, int S, cudaStream_t stream, const float *noise = nullptr, const double *stats = nullptr,
+              float noise_scale = 0.f);
+bool dp_noise_supported(const float *neg_cent, const float *noise, int S);
 int lengths_launch(const float *mask, int32_t *t_ys, int32_t *t_xs, int B, int T, int S, cudaStream_t stream);
 int expand_launch(const int32_t *idx, void *path_out, int path_dtype, int B, int T, int S, cudaStream_t stream);
 // mas_cost.cu
@@ -191,12 +193,15 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
     rc = cost_launch(z_p, m_p, logs_p, nc, noise ? stats : nullptr, neg_cent_out ? nullptr : t_ys, ws, cost_ws, B, D,
                      T, S, st);
     if (rc) return rc;
-    if (noise) {
+    if (noise && (neg_cent_out || !dp_noise_supported(nc, noise, S))) {
+        // the caller wants the noised cost plane itself (or the rows are not 16-byte): one more pass
         rc = add_noise_launch(nc, noise, stats, noise_scale, nc, (size_t)B * T * S, st);
         if (rc) return rc;
+        noise = nullptr;
     }
+    // otherwise the DP adds (std * noise) * scale while the cost streams in
     return dp_launch(nc, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T, S,
-                     st);
+                     st, noise, stats, noise_scale);
 }
 
 int mas_debug_read_trace(unsigned long long *host_out, int n_words)

@@ -138,8 +138,7 @@ __global__ void mas_add_noise_kernel(const float *__restrict__ nc, const float *
     const float sd = (float)sqrt(var);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float eps = (sd * noise[i]) * scale;
-        out[i] = nc[i] + eps;
+        out[i] = __fadd_rn(nc[i], __fmul_rn(__fmul_rn(sd, noise[i]), scale));  // rounded after every operation
     }
 }
 

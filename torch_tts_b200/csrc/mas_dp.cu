@@ -13,7 +13,8 @@ static int env_int(const char *name, int dflt)
 // ---------------------------------------------------------------------------
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
-bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool bits_smem, bool hop_smem, size_t budget)
+bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool bits_smem, bool hop_smem, size_t budget,
+                 bool with_noise)
 {
     const int S_pad = W * 32 * C;
     const int n_blk = (T + kCheck - 1) / kCheck;  // 32-row blocks of decision words
@@ -30,6 +31,8 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     p.off_hop = (uint32_t)off;
     if (hop_smem) off += align_up((size_t)hop_rows * S_pad, 16);
     p.stage_bytes = (uint32_t)align_up((size_t)R * S * 4 + 16 + 64, 128);  // tile + misalignment + zeroed pad
+    p.noise_off = with_noise ? p.stage_bytes : 0;                          // the noise tile follows the cost tile
+    if (with_noise) p.stage_bytes *= 2;
     off = align_up(off, 128);
     p.off_stage = (uint32_t)off;
     off += (size_t)stages * p.stage_bytes;
@@ -68,7 +71,7 @@ int dp_team_warps(int S)
     return W;
 }
 
-bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R, size_t budget)
+bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R, size_t budget, bool with_noise)
 {
     const int W = dp_team_warps(S);
     const int C = (S + W * 32 - 1) / (W * 32);
@@ -81,7 +84,7 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R, size_
         // without prefetch distance); on-chip bits / hops are only worth it with two stages to spare
         const int min_stages = (mode == 2) ? W : W + 2;
         for (int st = (stages_hint > 0 ? stages_hint : 6); st >= min_stages && !ok; --st) {
-            ok = dp_plan_try(pl, T, S, W, C, R, st, bits_smem, hop_smem, budget);
+            ok = dp_plan_try(pl, T, S, W, C, R, st, bits_smem, hop_smem, budget, with_noise);
             if (stages_hint > 0) break;
         }
     }
@@ -91,14 +94,14 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R, size_
     return true;
 }
 
-template <int C, int R, int W, bool kVec>
+template <int C, int R, int W, bool kVec, bool kNoise>
 __global__ void __launch_bounds__(dp_threads(W), 1) mas_dp_kernel(const DpParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
     uint32_t g_base = 0;
     dp_role_init(p, smem, threadIdx.x, kDpBar);
-    dp_role<C, R, W, kVec>(p, smem, b, blockIdx.x, g_base, threadIdx.x, kDpBar);
+    dp_role<C, R, W, kVec, kNoise>(p, smem, b, blockIdx.x, g_base, threadIdx.x, kDpBar);
 }
 
 // ---------------------------------------------------------------------------
@@ -169,23 +172,32 @@ __global__ void mas_expand_kernel(const int32_t *__restrict__ idx, unsigned char
 
 size_t dp_workspace_bytes(int B, int T, int S)
 {
-    DpPlan pl{};
-    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), 0, kSmemBudget)) return 0;
-    return align_up((size_t)B * 4, 256) + align_up(pl.ws_bits_bytes, 256) + align_up(pl.ws_hop_bytes, 256);
+    // the larger of the plans without / with a noise tile per stage (fewer stages may move the bits off chip)
+    size_t bits = 0, hop = 0;
+    for (int noise = 0; noise < 2; ++noise) {
+        DpPlan pl{};
+        if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), 0, kSmemBudget, noise != 0)) {
+            if (!noise) return 0;
+            continue;
+        }
+        bits = pl.ws_bits_bytes > bits ? pl.ws_bits_bytes : bits;
+        hop = pl.ws_hop_bytes > hop ? pl.ws_hop_bytes : hop;
+    }
+    return align_up((size_t)B * 4, 256) + align_up(bits, 256) + align_up(hop, 256);
 }
 
-template <int C, int R, int W, bool kVec>
+template <int C, int R, int W, bool kVec, bool kNoise>
 static int launch_dp_cv(const DpPlan &pl, cudaStream_t stream)
 {
     static thread_local int configured_dev = -1;
     int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     if (dev != configured_dev) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C, R, W, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C, R, W, kVec, kNoise>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kSmemBudget));
         configured_dev = dev;
     }
-    mas_dp_kernel<C, R, W, kVec><<<pl.p.B, dp_threads(W), pl.smem_bytes, stream>>>(pl.p);
+    mas_dp_kernel<C, R, W, kVec, kNoise><<<pl.p.B, dp_threads(W), pl.smem_bytes, stream>>>(pl.p);
     note_launch();
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;
@@ -196,23 +208,33 @@ static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
 {
     // vector cost loads need every tile row 16-byte aligned in shared memory
     const bool vec = (pl.p.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(pl.p.neg_cent) & 15) == 0);
-    return vec ? launch_dp_cv<C, R, W, true>(pl, stream) : launch_dp_cv<C, R, W, false>(pl, stream);
+    if (pl.p.noise) {
+        // noise applied while the cost streams in: vector path only (dp_noise_supported)
+        if (!vec || (reinterpret_cast<uintptr_t>(pl.p.noise) & 15)) return MAS_ERR_UNSUPPORTED_SHAPE;
+        return launch_dp_cv<C, R, W, true, true>(pl, stream);
+    }
+    return vec ? launch_dp_cv<C, R, W, true, false>(pl, stream) : launch_dp_cv<C, R, W, false, false>(pl, stream);
 }
 
 // fills pl (shared-memory plan + parameters) without launching; `order_out` receives the workspace slot
 // of the launch-order array
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
-               size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget)
+               size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget,
+               bool with_noise)
 {
     pl = DpPlan{};
-    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), R, smem_budget ? smem_budget : (size_t)kSmemBudget))
+    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), R, smem_budget ? smem_budget : (size_t)kSmemBudget,
+                      with_noise))
         return MAS_ERR_UNSUPPORTED_SHAPE;
     const size_t need = dp_workspace_bytes(B, T, S);
     if (need && (!workspace || workspace_bytes < need)) return MAS_ERR_WORKSPACE;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     DpParams &p = pl.p;
     p.neg_cent = neg_cent;
+    p.noise = nullptr;
+    p.stats = nullptr;
+    p.noise_scale = 0.f;
     p.t_ys = t_ys;
     p.t_xs = t_xs;
     p.path = static_cast<unsigned char *>(path_out);
@@ -237,16 +259,27 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
     return MAS_OK;
 }
 
+// noise applied inside the DP needs 16-byte rows and pointers (vector cost loads)
+bool dp_noise_supported(const float *neg_cent, const float *noise, int S)
+{
+    return (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(neg_cent) | reinterpret_cast<uintptr_t>(noise)) & 15) == 0;
+}
+
+// noise != nullptr: align neg_cent + (std * noise) * noise_scale without materialising it; stats = {sum, sum of
+// squares} of all cost cells on the device (the contraction's epilogue wrote them)
 int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
               int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace, size_t workspace_bytes, int B,
-              int T, int S, cudaStream_t stream)
+              int T, int S, cudaStream_t stream, const float *noise, const double *stats, float noise_scale)
 {
     DpPlan pl;
     int32_t *order = nullptr;
     int rc = dp_prepare(pl, neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, workspace,
-                        workspace_bytes, B, T, S, &order, 0, 0);
+                        workspace_bytes, B, T, S, &order, 0, 0, noise != nullptr);
     if (rc) return rc;
     DpParams &p = pl.p;
+    p.noise = noise;
+    p.stats = stats;
+    p.noise_scale = noise_scale;
     // Length bucketing: when the batch is more than one wave of CTAs, launch the
     // longest utterances first so short ones fill in behind them.
     int dev = 0, sms = 148;

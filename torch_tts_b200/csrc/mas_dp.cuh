@@ -48,6 +48,10 @@ __host__ __device__ constexpr int dp_chunk_rows(int S) { return S <= 256 ? 32 : 
 
 struct DpParams {
     const float *neg_cent;
+    const float *noise;      // nullable: VITS2 noise draw [B,T,S]; the DP then aligns neg_cent + (std * noise) * noise_scale
+    const double *stats;     // with noise: {sum, sum of squares} of all B*T*S cost cells (device)
+    float noise_scale;
+    uint32_t noise_off;      // with noise: byte offset of the noise tile inside a stage
     const int32_t *t_ys;
     const int32_t *t_xs;
     const int32_t *order;  // nullable: CTA -> utterance (longest first)
@@ -116,11 +120,17 @@ __device__ __forceinline__ void store_one(unsigned char *path_b, size_t cell, in
 //   kExact  false: max via FMNMX (short dependency chain); exact while every cost is
 //           finite, which `fin` tracks.
 //           true: the reference's compare-select, bit-for-bit also for NaN/Inf input.
-template <int C, int NR, bool kEdge, bool kVec, bool kExact>
+//   kNoise  the stage also holds the noise tile (nz_off floats behind the cost tile): the cost of a cell is
+//           nc + (sd * noise) * scale, rounded after every operation like the reference (models.py:1241-1247)
+struct DpNoise {
+    int nz_off;
+    float sd, scale;
+};
+template <int C, int NR, bool kEdge, bool kVec, bool kExact, bool kNoise>
 __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *trow,
                                         int S, int bit0, float &carry_v, int &carry_o, const float *bin_v,
                                         const int *bin_o, float *bout_v, int *bout_o, int y, int x0, bool lane0,
-                                        bool lane31)
+                                        bool lane31, const DpNoise &nz)
 {
     float cost[NR][C];
     float lv[NR + 1];
@@ -146,6 +156,29 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
         } else {
 #pragma unroll
             for (int k = 0; k < C; ++k) cost[i][k] = src[k];
+        }
+        if (kNoise) {
+            const float *nsrc = src + nz.nz_off;
+            float n_[C];
+            if (kVec && C % 4 == 0) {
+#pragma unroll
+                for (int k = 0; k < C; k += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(nsrc + k);
+                    n_[k] = t.x, n_[k + 1] = t.y, n_[k + 2] = t.z, n_[k + 3] = t.w;
+                }
+            } else if (kVec && C % 2 == 0) {
+#pragma unroll
+                for (int k = 0; k < C; k += 2) {
+                    const float2 t = *reinterpret_cast<const float2 *>(nsrc + k);
+                    n_[k] = t.x, n_[k + 1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < C; ++k) n_[k] = nsrc[k];
+            }
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+                cost[i][k] = __fadd_rn(cost[i][k], __fmul_rn(__fmul_rn(nz.sd, n_[k]), nz.scale));
         }
     }
     if (NR == 4) {
@@ -224,10 +257,11 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
 }
 
 // one chunk (<= R rows) of this warp's columns; bin/bout point at the ring slot of the chunk's first row
-template <int C, int R, bool kEdge, bool kVec, bool kExact>
+template <int C, int R, bool kEdge, bool kVec, bool kExact, bool kNoise>
 __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *tile,
                                          int S, int rows, int row0, float &carry_v, int &carry_o, const float *bin_v,
-                                         const int *bin_o, float *bout_v, int *bout_o, int x0, bool lane0, bool lane31)
+                                         const int *bin_o, float *bout_v, int *bout_o, int x0, bool lane0, bool lane31,
+                                         const DpNoise &nz)
 {
     // Threads whose columns lie past S re-read the last real columns instead of whatever
     // follows the row: their results are never used, but they must not invent NaNs.
@@ -243,11 +277,11 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
         uint32_t w8[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) w8[k] = 0u;
-        dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
-                                           bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
-        dp_rows<C, 4, kEdge, kVec, kExact>(v, org, fin, w8, trow + (size_t)(r + 4) * S, S, 4, carry_v, carry_o,
+        dp_rows<C, 4, kEdge, kVec, kExact, kNoise>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
+                                           bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31, nz);
+        dp_rows<C, 4, kEdge, kVec, kExact, kNoise>(v, org, fin, w8, trow + (size_t)(r + 4) * S, S, 4, carry_v, carry_o,
                                            bin_v + r + 4, bin_o + r + 4, bout_v + r + 4, bout_o + r + 4, row0 + r + 4, x0,
-                                           lane0, lane31);
+                                           lane0, lane31, nz);
 #pragma unroll
         for (int k = 0; k < C; ++k) wl[k] |= w8[k] << r;
     }
@@ -256,8 +290,8 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
         uint32_t w8[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) w8[k] = 0u;
-        dp_rows<C, 1, kEdge, kVec, kExact>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
-                                           bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31);
+        dp_rows<C, 1, kEdge, kVec, kExact, kNoise>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
+                                           bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31, nz);
 #pragma unroll
         for (int k = 0; k < C; ++k) wl[k] |= w8[k] << r;
     }
@@ -294,7 +328,7 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
 // Aligns utterance b.  Runs on the dp_threads(W) threads of one team; `slot` selects the team's region of
 // the spill workspace; g_base is the running cost-tile counter of this CTA's stage ring (mbarrier phases
 // continue across utterances).
-template <int C, int R, int W, bool kVec>
+template <int C, int R, int W, bool kVec, bool kNoise = false>
 __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
                                         int bar)
 {
@@ -341,6 +375,17 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
 
     constexpr int ring = 2 * R;
     const uint32_t n_stages = (uint32_t)p.stages;
+    DpNoise nzp{0, 0.f, 0.f};
+    if (kNoise) {
+        // unbiased std over ALL cells, padding included (torch.std default, models.py:1243), from fp64 sums
+        const double n = (double)p.B * (double)plane;
+        const double mean = p.stats[0] / n;
+        double var = (p.stats[1] - p.stats[0] * mean) / (n > 1.0 ? n - 1.0 : 1.0);
+        if (var < 0) var = 0;
+        nzp.sd = (float)sqrt(var);
+        nzp.scale = p.noise_scale;
+        nzp.nz_off = (int)(p.noise_off / 4);
+    }
     int *nonfinite_s = reinterpret_cast<int *>(smem + p.off_misc);
     if (tid == 0) *nonfinite_s = 0;
     bar_sync(bar, kThreads);  // previous utterance's backtrack is done with the shared buffers
@@ -390,8 +435,23 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                             (o < want) ? *reinterpret_cast<const float *>(src + o) : 0.0f;
                 }
                 if (p.debug & 4) bulk = 0;
-                mbar_arrive_expect_tx(&full[st], bulk);
-                if (bulk) bulk_g2s(dst, src, bulk, &full[st]);
+                if (kNoise) {
+                    // the noise tile of the same cells, nz_off behind the cost tile (same padding / tail rules)
+                    unsigned char *ndst = dst + p.noise_off;
+                    const unsigned char *nsrc = reinterpret_cast<const unsigned char *>(p.noise) + src0;
+                    *reinterpret_cast<uint4 *>(ndst + ((want + 15u) & ~15u)) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(ndst + ((want + 15u) & ~15u) + 16) = make_uint4(0, 0, 0, 0);
+                    for (uint32_t o = bulk; o < ((want + 15u) & ~15u); o += 4)
+                        *reinterpret_cast<float *>(ndst + o) = (o < want) ? *reinterpret_cast<const float *>(nsrc + o) : 0.0f;
+                    mbar_arrive_expect_tx(&full[st], 2 * bulk);
+                    if (bulk) {
+                        bulk_g2s(dst, src, bulk, &full[st]);
+                        bulk_g2s(ndst, nsrc, bulk, &full[st]);
+                    }
+                } else {
+                    mbar_arrive_expect_tx(&full[st], bulk);
+                    if (bulk) bulk_g2s(dst, src, bulk, &full[st]);
+                }
             };
             if (lane == 0) {
                 const int pre = min((int)n_stages, n_chunks);
@@ -472,8 +532,9 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     if (p.trace) d1 = clock64();
                     const bool edge = row0 < edge_rows;
 #define MAS_CHUNK(EDGE, EXACT)                                                                             \
-    dp_chunk<C, R, EDGE, kVec, EXACT>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o, bin_v + slot0, \
-                                   bin_o + slot0, bout_v + slot0, bout_o + slot0, x0, lane0, lane31)
+    dp_chunk<C, R, EDGE, kVec, EXACT, kNoise>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o,        \
+                                              bin_v + slot0, bin_o + slot0, bout_v + slot0, bout_o + slot0, x0,  \
+                                              lane0, lane31, nzp)
                     if (p.debug & 2) {
                     } else if (pass == 0) {
                         if (edge)
@@ -659,6 +720,7 @@ int dp_team_warps(int S);
 size_t dp_workspace_bytes(int B, int T, int S);
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
-               size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget);
+               size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget,
+               bool with_noise = false);
 
 }  // namespace mas
