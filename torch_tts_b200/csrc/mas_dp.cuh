@@ -516,19 +516,18 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             int *bout_o = bnd_o + (size_t)(w + 1) * ring;
             const int edge_rows = (w + 1) * 32 * C;  // rows where a column of this warp is still above the diagonal
             long long dacc[4] = {0, 0, 0, 0};  // diagnostics: cycles in tile wait, compute, bits/hop, barrier
+            uint32_t st = g0 % n_stages, st_par = (g0 / n_stages) & 1u;  // stage / mbarrier parity of chunk 0, then stepped
             for (int step = 0; step < n_steps; ++step) {
                 const int c = step - w;
                 long long d0 = p.trace ? clock64() : 0, d1 = d0, d2 = d0, d3 = d0;
                 if (c >= 0 && c < n_chunks) {
-                    const uint32_t g = g0 + c;
-                    const uint32_t st = g % n_stages;
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
                     const int slot0 = (c & 1) * R;
                     const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
                     const float *tile =
                         reinterpret_cast<const float *>(smem + p.off_stage + (size_t)st * p.stage_bytes + mis);
-                    mbar_wait(&full[st], (g / n_stages) & 1u);
+                    mbar_wait(&full[st], st_par);
                     if (p.trace) d1 = clock64();
                     const bool edge = row0 < edge_rows;
 #define MAS_CHUNK(EDGE, EXACT)                                                                             \
@@ -590,6 +589,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
                     }
                     if (p.trace) d3 = clock64();
+                    if (++st == n_stages) st = 0, st_par ^= 1u;
                 }
                 bar_sync(bar, kThreads);
                 if (p.trace) {
