@@ -45,7 +45,7 @@ enum {
     MAS_OK = 0,
     MAS_ERR_NULL_POINTER = 1,
     MAS_ERR_BAD_SHAPE = 2,        /* B, T, S or D < 1 */
-    MAS_ERR_UNSUPPORTED_SHAPE = 3,/* S > MAS_MAX_TEXT, T > MAS_MAX_MEL, D not supported */
+    MAS_ERR_UNSUPPORTED_SHAPE = 3,/* S > MAS_MAX_TEXT, T > MAS_MAX_MEL */
     MAS_ERR_ALIGNMENT = 4,        /* a base pointer is not 16-byte aligned */
     MAS_ERR_WORKSPACE = 5,        /* workspace NULL or smaller than the *_workspace_bytes() answer */
     MAS_ERR_BAD_DTYPE = 6,
@@ -119,7 +119,10 @@ int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p,
  *     [B,T,S] float32 supplied by the caller (models.py:1244); the library
  *     computes std over all B*T*S cells (unbiased, padding included, :1243)
  *     and adds (std * noise) * noise_scale (:1242-1247).
- *   - neg_cent_out: optional [B,T,S] float32 copy of the cost actually aligned.
+ *   - neg_cent_out: optional [B,T,S] float32 copy of the cost actually aligned (with noise: the noised
+ *     cost; without this request the noised plane is never written -- the DP adds the noise on the fly).
+ *   - no noise, S <= 256, S % 4 == 0, T % 4 == 0: ONE kernel runs contraction and DP concurrently
+ *     (cooperative launch; needs the whole GPU like any persistent kernel).
  */
 size_t mas_fused_align_workspace_bytes(int B, int D, int T, int S, int with_noise);
 int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,

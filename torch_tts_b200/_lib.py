@@ -13,7 +13,7 @@ import threading
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmas_b200.so")
+LIB_PATH = os.environ.get("MAS_LIB_PATH") or os.path.join(HERE, "libmas_b200.so")   # override: kernel experiments
 
 # every symbol include/mas_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = (

@@ -1,34 +1,57 @@
-"""In-tree build of libmas_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+"""In-tree build of libmas_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+Every .cu is compiled to an object in parallel, then linked into one shared library."""
 from __future__ import annotations
 
+import concurrent.futures
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libmas_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _compile(args):
+    nvcc, src, obj, verbose = args
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r.returncode, r.stdout + r.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sources()
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(HERE, "..", "include", "mas_b200.h"))
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
-        return OUT
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "mas_b200.h"))
+    newest_header = max(os.path.getmtime(h) for h in headers)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode:
-        sys.stderr.write(r.stdout + r.stderr)
+    os.makedirs(OBJ, exist_ok=True)
+    jobs, objs = [], []
+    for src in srcs:
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header)
+        if stale:
+            jobs.append((nvcc, src, obj, verbose))
+    if not jobs and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(o) for o in objs):
+        return OUT
+    with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        for src, rc, log in ex.map(_compile, jobs):
+            if verbose or rc:
+                sys.stderr.write(log)
+            if rc:
+                raise RuntimeError(f"nvcc failed on {os.path.basename(src)}")
+    r = subprocess.run([nvcc, "-shared", "-o", OUT] + objs, capture_output=True, text=True)
     if r.returncode:
-        raise RuntimeError("nvcc failed building libmas_b200.so")
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking libmas_b200.so")
     return OUT
 
 

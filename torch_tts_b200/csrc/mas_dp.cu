@@ -66,8 +66,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
 int dp_team_warps(int S)
 {
     int W = S <= 512 ? 2 : 4;
-    const int e = env_int("MAS_DP_WARPS", 0);
-    if (e == 4 || (e == 2 && S <= 512)) W = e;
+    if (env_int("MAS_DP_WARPS", 0) == 4 && S > 128 && S <= 256) W = 4;  // experiments: 4 warps x 2 columns per thread
     return W;
 }
 
@@ -298,7 +297,7 @@ int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, v
     if (pl.C == CC && p.R == RR && p.W == WW) return launch_dp_c<CC, RR, WW>(pl, stream);
     MAS_DP_CASE(1, 32, 2) MAS_DP_CASE(2, 32, 2) MAS_DP_CASE(3, 32, 2) MAS_DP_CASE(4, 32, 2)
     MAS_DP_CASE(5, 16, 2) MAS_DP_CASE(6, 16, 2) MAS_DP_CASE(7, 16, 2) MAS_DP_CASE(8, 16, 2)
-    MAS_DP_CASE(1, 32, 4) MAS_DP_CASE(2, 32, 4) MAS_DP_CASE(3, 16, 4) MAS_DP_CASE(4, 16, 4)
+    MAS_DP_CASE(2, 32, 4)   // MAS_DP_WARPS=4 at S <= 256: the A/B partner of the default
     MAS_DP_CASE(5, 8, 4) MAS_DP_CASE(6, 8, 4) MAS_DP_CASE(7, 8, 4) MAS_DP_CASE(8, 8, 4)
 #undef MAS_DP_CASE
     return MAS_ERR_UNSUPPORTED_SHAPE;

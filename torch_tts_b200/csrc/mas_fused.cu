@@ -190,7 +190,6 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     else MAS_FUSED_CASE(2, 2)
     else MAS_FUSED_CASE(3, 2)
     else MAS_FUSED_CASE(4, 2)
-    else MAS_FUSED_CASE(1, 4)
     else MAS_FUSED_CASE(2, 4)
     else return MAS_ERR_UNSUPPORTED_SHAPE;
 #undef MAS_FUSED_CASE
