@@ -43,6 +43,8 @@ for k in range(8):
     a = rel(dp[:, 2 + k])
     print(f"tile {k} acquired: min {a.min():7.1f} mean {a.mean():7.1f} max {a.max():7.1f}")
 print("forward end: min %.1f mean %.1f max %.1f" % (rel(dp[:, 1]).min(), rel(dp[:, 1]).mean(), rel(dp[:, 1]).max()))
+for name, k in (("level-1 hops done", 26), ("level-2 walks done", 27), ("zero flag seen", 28)):
+    print("%-18s min %.1f mean %.1f max %.1f" % (name + ":", rel(dp[:, k]).min(), rel(dp[:, k]).mean(), rel(dp[:, k]).max()))
 print("outputs end: min %.1f mean %.1f max %.1f" % (rel(dp[:, 30]).min(), rel(dp[:, 30]).mean(), rel(dp[:, 30]).max()))
 tr = buf[40960:40960 + B * 16].reshape(B, 16).astype(np.int64)
 n_steps = (T + 31) // 32 + 3

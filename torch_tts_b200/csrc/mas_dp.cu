@@ -70,22 +70,30 @@ int dp_team_warps(int S)
     return W;
 }
 
-bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R, size_t budget, bool with_noise)
+bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, size_t budget, bool with_noise)
 {
     const int W = dp_team_warps(S);
     const int C = (S + W * 32 - 1) / (W * 32);
     if (C < 1 || C > 8) return false;
-    if (R <= 0) R = dp_chunk_rows(S);
+    // Chunk height: every chunk step costs a fixed ~700 cycles (barrier, mbarrier wait, bookkeeping), so take
+    // the tallest chunk whose ring still fits: dp_chunk_rows(S) with bits / hops on chip, else up to twice
+    // that once they are spilled anyway (long utterances).
+    const int R0 = R_hint > 0 ? R_hint : dp_chunk_rows(S);
     bool ok = false;
     for (int mode = 0; mode < 3 && !ok; ++mode) {
         const bool bits_smem = (mode == 0), hop_smem = (mode <= 1);
         // the W DP warps work on W consecutive chunks at once, so the ring needs at least W stages (then
         // without prefetch distance); on-chip bits / hops are only worth it with two stages to spare
-        const int min_stages = (mode == 2) ? W : W + 2;
-        for (int st = (stages_hint > 0 ? stages_hint : 6); st >= min_stages && !ok; --st) {
-            ok = dp_plan_try(pl, T, S, W, C, R, st, bits_smem, hop_smem, budget, with_noise);
-            if (stages_hint > 0) break;
-        }
+        const int min_stages = (mode == 2) ? W + 1 : W + 2;
+        for (int R = (mode == 2 && R_hint <= 0 && R0 < 32) ? 2 * R0 : R0; R >= R0 && !ok; R /= 2)
+            for (int st = (stages_hint > 0 ? stages_hint : 6); st >= min_stages && !ok; --st) {
+                ok = dp_plan_try(pl, T, S, W, C, R, st, bits_smem, hop_smem, budget, with_noise);
+                if (stages_hint > 0) break;
+            }
+    }
+    if (!ok) {
+        // last resort: no prefetch distance at all
+        ok = dp_plan_try(pl, T, S, W, C, R0, W, false, false, budget, with_noise);
     }
     if (!ok) return false;
     pl.ws_bits_bytes = pl.p.bits_in_smem ? 0 : (size_t)B * pl.p.bits_words_per_cta * 4;
@@ -299,6 +307,8 @@ int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, v
     MAS_DP_CASE(5, 16, 2) MAS_DP_CASE(6, 16, 2) MAS_DP_CASE(7, 16, 2) MAS_DP_CASE(8, 16, 2)
     MAS_DP_CASE(2, 32, 4)   // MAS_DP_WARPS=4 at S <= 256: the A/B partner of the default
     MAS_DP_CASE(5, 8, 4) MAS_DP_CASE(6, 8, 4) MAS_DP_CASE(7, 8, 4) MAS_DP_CASE(8, 8, 4)
+    MAS_DP_CASE(5, 16, 4) MAS_DP_CASE(6, 16, 4) MAS_DP_CASE(7, 16, 4) MAS_DP_CASE(8, 16, 4)   // bits / hops spilled
+    MAS_DP_CASE(5, 32, 2) MAS_DP_CASE(6, 32, 2) MAS_DP_CASE(7, 32, 2) MAS_DP_CASE(8, 32, 2)
 #undef MAS_DP_CASE
     return MAS_ERR_UNSUPPORTED_SHAPE;
 }

@@ -42,6 +42,8 @@ constexpr int kCheck = 32;  // checkpoint interval (rows)
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kDpBar = 3;     // named barrier of the DP role (kThreads threads)
 constexpr int kZeroBytes = 8192;  // zeroed shared buffer the path zero-fill bulk-stores from
+constexpr uint32_t kZeroFillBuf = 32768;  // zero page of the zero-fill role (contraction CTAs that ran out of tiles)
+constexpr int kZeroParts = 8;             // slices per path plane handed out by the zero-fill role
 
 // mel rows per chunk (= per TMA tile) for S text columns: a stage stays <= 32 KB
 __host__ __device__ constexpr int dp_chunk_rows(int S) { return S <= 256 ? 32 : (S <= 512 ? 16 : 8); }
@@ -627,6 +629,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             entry_s[j - 1] = (uint16_t)c;
         }
         idx_s[0] = 0;
+        if (p.trace) p.trace[12288 + (size_t)b * 32 + 26] = globaltimer_ns();
     }
     bar_sync(bar, kThreads);
     // level 2: independent walks of <= 32 rows, one per thread
@@ -647,12 +650,14 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         }
     }
     for (int x = tid; x < S_pad; x += kThreads) end_s[x] = -1;
+    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 27] = globaltimer_ns();
     if (p.zero_flags && tid == 0) {
         // somebody else zero-fills this utterance's path plane: the ones may only follow the zeros
         uint32_t *f = p.zero_flags + b;
-        while (ld_acquire_gpu(f) == 0u) __nanosleep(64);
+        while (ld_acquire_gpu(f) < (uint32_t)kZeroParts) __nanosleep(64);
         *f = 0u;
     }
+    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 28] = globaltimer_ns();
     bar_sync(bar, kThreads);
 
     // =================== outputs ===================
@@ -679,7 +684,6 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
 // Zero-fills the dense path planes of utterances first, first + step, ... and raises their zero flag.
 // Runs on a whole CTA that has nothing else left to do (fused kernel); `zbuf` is kZeroFillBuf bytes of
 // shared memory.  The DP role of the utterance's owner waits for the flag before it scatters the ones.
-constexpr uint32_t kZeroFillBuf = 32768;
 __device__ __forceinline__ void zero_fill_role(const DpParams &p, unsigned char *zbuf, int first, int step)
 {
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -687,31 +691,44 @@ __device__ __forceinline__ void zero_fill_role(const DpParams &p, unsigned char 
     fence_proxy_async();
     __syncthreads();
     const size_t pbytes = (size_t)p.T * p.S * path_elem_size(p.path_dtype);
-    for (int b = first; b < p.B; b += step) {
+    const size_t part_bytes = align_up((pbytes + kZeroParts - 1) / kZeroParts, 512);
+    // work item = one of kZeroParts slices of one utterance's plane, so that all helper CTAs stay busy.
+    // Pass 1 issues every store of this CTA (nothing waits in between), pass 2 raises the flags.
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(p.path) | pbytes) & 15) == 0;
+    for (int wi = first; wi < p.B * kZeroParts; wi += step) {
+        const int b = wi / kZeroParts, part = wi - b * kZeroParts;
         unsigned char *path_b = p.path + (size_t)b * pbytes;
-        const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
+        size_t lo = (size_t)part * part_bytes, hi = lo + part_bytes;
+        if (lo > pbytes) lo = pbytes;
+        if (hi > pbytes) hi = pbytes;
+        if (hi <= lo) continue;
         if (bulk_ok) {
-            if (tid == 0) {
-                for (size_t o = 0; o < pbytes; o += kZeroFillBuf)
-                    bulk_s2g(path_b + o, zbuf, (uint32_t)min((size_t)kZeroFillBuf, pbytes - o));
-                bulk_commit();
-                bulk_wait_all();
-                fence_proxy_async_all();
-            }
+            if (tid == 0)
+                for (size_t o = lo; o < hi; o += kZeroFillBuf)
+                    bulk_s2g(path_b + o, zbuf, (uint32_t)min((size_t)kZeroFillBuf, hi - o));
         } else {
             const int warp = tid >> 5, n_warps = nthr >> 5;
-            const size_t seg = align_up((pbytes + n_warps - 1) / n_warps, 512);
-            size_t lo = (size_t)warp * seg, hi = lo + seg;
-            if (lo > pbytes) lo = pbytes;
-            if (hi > pbytes) hi = pbytes;
-            if (hi > lo) zero_bytes_warp(path_b + lo, hi - lo, tid & 31);
-            __threadfence();
+            const size_t seg = align_up((hi - lo + n_warps - 1) / n_warps, 512);
+            size_t a = lo + (size_t)warp * seg, e = a + seg;
+            if (a > hi) a = hi;
+            if (e > hi) e = hi;
+            if (e > a) zero_bytes_warp(path_b + a, e - a, tid & 31);
         }
-        __syncthreads();
+    }
+    if (bulk_ok) {
         if (tid == 0) {
-            __threadfence();
-            st_release_gpu(p.zero_flags + b, 1u);
+            bulk_commit();
+            bulk_wait_all();
+            fence_proxy_async_all();
         }
+    } else {
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        for (int wi = first; wi < p.B * kZeroParts; wi += step)
+            atomicAdd(p.zero_flags + wi / kZeroParts, 1u);  // the DP waits for all kZeroParts slices
     }
 }
 
