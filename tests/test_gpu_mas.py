@@ -160,3 +160,14 @@ def test_full_size_invariants(cuda_device):
     sample = [0, 1, 100, 255, 511]
     want = mas_oracle.maximum_path_c(nc[sample].cpu().numpy(), t_y[sample].numpy(), t_x[sample].numpy())
     assert np.array_equal(path[sample].cpu().numpy().astype(np.int32), want)
+
+
+@pytest.mark.parametrize("B,S,T,ties", [(4, 256, 1024, False), (3, 100, 333, True), (5, 64, 64, False), (2, 200, 40 * 32 + 1, True)])
+def test_value_bookkeeping_warp_split(cuda_device, monkeypatch, B, S, T, ties):
+    """MAS_DP_VK=1: the experimental warp-specialised DP (value warps + bookkeeping warps) is bit-exact too."""
+    monkeypatch.setenv("MAS_DP_VK", "1")
+    nc = synthetic.neg_cent_like(B, S, T, seed=S + T, ties=ties)
+    t_x, t_y = synthetic.ragged_lengths(B, S, T, seed=B)
+    t_y = torch.maximum(t_y, t_x)
+    nc[0, T // 3, S // 2] = float("nan")          # the exact second pass as well
+    _check(nc, t_x, t_y, cuda_device)

@@ -14,7 +14,7 @@ static int env_int(const char *name, int dflt)
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
 bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool bits_smem, bool hop_smem, size_t budget,
-                 bool with_noise)
+                 bool with_noise, bool vk)
 {
     const int S_pad = W * 32 * C;
     const int n_blk = (T + kCheck - 1) / kCheck;  // 32-row blocks of decision words
@@ -23,6 +23,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     DpParams &p = pl.p;
     p.R = R;
     p.W = W;
+    p.vk = vk ? 1 : 0;
     p.stages = stages;
     p.off_bar = (uint32_t)off;
     off += 128;
@@ -36,8 +37,12 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     off = align_up(off, 128);
     p.off_stage = (uint32_t)off;
     off += (size_t)stages * p.stage_bytes;
+    p.off_vring = (uint32_t)off;
+    if (vk) off += (size_t)(2 * R + 4) * S_pad * 4;   // values of the last 2R rows + the last rows of 4 chunks
+    p.off_kring0 = (uint32_t)off;
+    if (vk) off += (size_t)4 * R * 4;
     p.off_bnd_v = (uint32_t)off;
-    off += (size_t)(W + 1) * 2 * R * 4;
+    off += (size_t)(W + 1) * (vk ? 4 : 2) * R * 4;
     p.off_bnd_o = (uint32_t)off;
     off += (size_t)(W + 1) * 2 * R * 4;
     p.off_zero = (uint32_t)off;
@@ -70,7 +75,7 @@ int dp_team_warps(int S)
     return W;
 }
 
-bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, size_t budget, bool with_noise)
+bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, size_t budget, bool with_noise, bool vk)
 {
     const int W = dp_team_warps(S);
     const int C = (S + W * 32 - 1) / (W * 32);
@@ -80,6 +85,13 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, 
     // that once they are spilled anyway (long utterances).
     const int R0 = R_hint > 0 ? R_hint : dp_chunk_rows(S);
     bool ok = false;
+    if (vk) {
+        // warp split: everything on chip, one tile of prefetch distance at least, or not at all
+        for (int st = 5; st >= W + 1 && !ok; --st) ok = dp_plan_try(pl, T, S, W, C, R0, st, true, true, budget, false, true);
+        if (!ok) return false;
+        pl.ws_bits_bytes = pl.ws_hop_bytes = 0;
+        return true;
+    }
     for (int mode = 0; mode < 3 && !ok; ++mode) {
         const bool bits_smem = (mode == 0), hop_smem = (mode <= 1);
         // the W DP warps work on W consecutive chunks at once, so the ring needs at least W stages (then
@@ -87,13 +99,13 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, 
         const int min_stages = (mode == 2) ? W + 1 : W + 2;
         for (int R = (mode == 2 && R_hint <= 0 && R0 < 32) ? 2 * R0 : R0; R >= R0 && !ok; R /= 2)
             for (int st = (stages_hint > 0 ? stages_hint : 6); st >= min_stages && !ok; --st) {
-                ok = dp_plan_try(pl, T, S, W, C, R, st, bits_smem, hop_smem, budget, with_noise);
+                ok = dp_plan_try(pl, T, S, W, C, R, st, bits_smem, hop_smem, budget, with_noise, false);
                 if (stages_hint > 0) break;
             }
     }
     if (!ok) {
         // last resort: no prefetch distance at all
-        ok = dp_plan_try(pl, T, S, W, C, R0, W, false, false, budget, with_noise);
+        ok = dp_plan_try(pl, T, S, W, C, R0, W, false, false, budget, with_noise, false);
     }
     if (!ok) return false;
     pl.ws_bits_bytes = pl.p.bits_in_smem ? 0 : (size_t)B * pl.p.bits_words_per_cta * 4;
@@ -101,14 +113,14 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, 
     return true;
 }
 
-template <int C, int R, int W, bool kVec, bool kNoise>
-__global__ void __launch_bounds__(dp_threads(W), 1) mas_dp_kernel(const DpParams p)
+template <int C, int R, int W, bool kVec, bool kNoise, bool kVK>
+__global__ void __launch_bounds__(dp_threads(W, kVK), 1) mas_dp_kernel(const DpParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
     uint32_t g_base = 0;
     dp_role_init(p, smem, threadIdx.x, kDpBar);
-    dp_role<C, R, W, kVec, kNoise>(p, smem, b, blockIdx.x, g_base, threadIdx.x, kDpBar);
+    dp_role<C, R, W, kVec, kNoise, kVK>(p, smem, b, blockIdx.x, g_base, threadIdx.x, kDpBar);
 }
 
 // ---------------------------------------------------------------------------
@@ -183,7 +195,7 @@ size_t dp_workspace_bytes(int B, int T, int S)
     size_t bits = 0, hop = 0;
     for (int noise = 0; noise < 2; ++noise) {
         DpPlan pl{};
-        if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), 0, kSmemBudget, noise != 0)) {
+        if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), 0, kSmemBudget, noise != 0, false)) {
             if (!noise) return 0;
             continue;
         }
@@ -193,18 +205,18 @@ size_t dp_workspace_bytes(int B, int T, int S)
     return align_up((size_t)B * 4, 256) + align_up(bits, 256) + align_up(hop, 256);
 }
 
-template <int C, int R, int W, bool kVec, bool kNoise>
+template <int C, int R, int W, bool kVec, bool kNoise, bool kVK = false>
 static int launch_dp_cv(const DpPlan &pl, cudaStream_t stream)
 {
     static thread_local int configured_dev = -1;
     int dev = 0;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     if (dev != configured_dev) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C, R, W, kVec, kNoise>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C, R, W, kVec, kNoise, kVK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kSmemBudget));
         configured_dev = dev;
     }
-    mas_dp_kernel<C, R, W, kVec, kNoise><<<pl.p.B, dp_threads(W), pl.smem_bytes, stream>>>(pl.p);
+    mas_dp_kernel<C, R, W, kVec, kNoise, kVK><<<pl.p.B, dp_threads(W, kVK), pl.smem_bytes, stream>>>(pl.p);
     note_launch();
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;
@@ -220,6 +232,13 @@ static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
         if (!vec || (reinterpret_cast<uintptr_t>(pl.p.noise) & 15)) return MAS_ERR_UNSUPPORTED_SHAPE;
         return launch_dp_cv<C, R, W, true, true>(pl, stream);
     }
+    if (pl.p.vk) {
+        if (!vec) return MAS_ERR_UNSUPPORTED_SHAPE;
+        if constexpr (W == 2 && R == 32)
+            return launch_dp_cv<C, R, W, true, false, true>(pl, stream);
+        else
+            return MAS_ERR_UNSUPPORTED_SHAPE;
+    }
     return vec ? launch_dp_cv<C, R, W, true, false>(pl, stream) : launch_dp_cv<C, R, W, false, false>(pl, stream);
 }
 
@@ -231,8 +250,14 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
                bool with_noise)
 {
     pl = DpPlan{};
-    if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), R, smem_budget ? smem_budget : (size_t)kSmemBudget,
-                      with_noise))
+    // value / bookkeeping warp split, EXPERIMENTAL (MAS_DP_VK=1 turns it on): S <= 256 with 16-byte rows, no noise,
+    // everything on chip.  The value warps alone run at ~24 cycles per mel row (2x the single-role warps), but two
+    // bookkeeping warps need ~47, so it is not the default yet.
+    bool vk = env_int("MAS_DP_VK", 0) && !with_noise && R == 0 && S <= 256 && S % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(neg_cent) & 15) == 0 && dp_team_warps(S) == 2 && dp_chunk_rows(S) == 32;
+    if (vk) vk = dp_make_plan(pl, B, T, S, 0, 0, smem_budget ? smem_budget : (size_t)kSmemBudget, false, true);
+    if (!vk && !dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), R,
+                             smem_budget ? smem_budget : (size_t)kSmemBudget, with_noise, false))
         return MAS_ERR_UNSUPPORTED_SHAPE;
     const size_t need = dp_workspace_bytes(B, T, S);
     if (need && (!workspace || workspace_bytes < need)) return MAS_ERR_WORKSPACE;

@@ -36,7 +36,7 @@ namespace mas {
 // thread has the instruction-level parallelism to hide the max -> add latency, and only every C-th
 // link of the dependency chain pays for a shuffle.  W = 4 serves S > 512.
 constexpr int kMaxDpWarps = 4;
-__host__ __device__ constexpr int dp_threads(int W) { return (W + 1) * 32; }  // + producer warp
+__host__ __device__ constexpr int dp_threads(int W, bool vk = false) { return ((vk ? 2 * W : W) + 1) * 32; }  // + producer warp
 constexpr int kMaxStages = 8;
 constexpr int kCheck = 32;  // checkpoint interval (rows)
 constexpr int kSmemBudget = 227 * 1024;
@@ -71,9 +71,12 @@ struct DpParams {
     int B, T, S;
     int R;       // mel rows per chunk (template parameter of the role; 32, 16 or 8)
     int W;       // DP warps per team (template parameter of the role; 2 or 4)
+    int vk;      // value / bookkeeping warp split (W value warps + W bookkeeping warps + producer)
+    uint32_t off_vring, off_kring0;  // vk: DP values of the last 2R rows [2R][S_pad]; left sentinel ring of column 0
     int stages;  // cost-tile ring depth (2..kMaxStages)
     int path_dtype;
-    int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads
+    int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads,
+                 // 16 / 32 warp split: bookkeeping / value warps idle
     int bits_in_smem, hop_in_smem;
     uint32_t off_bits, off_hop, off_stage, stage_bytes, off_bnd_v, off_bnd_o, off_idx, off_end, off_entry, off_bar, off_zero, off_misc;
     unsigned long long bits_words_per_cta, hop_bytes_per_cta;
@@ -299,6 +302,169 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
     }
 }
 
+// ---------------------------------------------------------------------------
+// value / bookkeeping split (kVK).  A DP warp is latency-bound: one in-order warp per scheduler exposes the
+// shuffle and max -> add latencies whatever else it has to issue.  Here the VALUE warps run only the
+// dependency chain (cost load, shuffle, max, add) and publish every row of DP values to a shared ring;
+// the BOOKKEEPING warps, on the other two schedulers and one chunk behind, turn those values into decision
+// bits, origins and checkpoints.  Both see exactly the operands of the reference's compare (core.pyx:28,32).
+// ---------------------------------------------------------------------------
+// NR rows of the value chain for this thread's C columns; vrow = &vring[slot(row y) * S_pad + x0], advanced
+// by the caller's slot arithmetic (rows of one call never wrap: calls start at multiples of 4 rows).
+template <int C, int NR, bool kEdge, bool kVec, bool kExact>
+__device__ __forceinline__ void v_rows(float (&v)[C], float &fin, const float *trow, int S, float &carry_v,
+                                       const float *bin_v, float *bout_v, float *vrow, int vpitch, int y, int x0,
+                                       bool lane0, bool lane31)
+{
+    float cost[NR][C];
+    float lv[NR + 1];
+    lv[0] = carry_v;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const float *src = trow + (size_t)i * S;
+        if (kVec && (C % 4 == 0)) {
+#pragma unroll
+            for (int k = 0; k < C; k += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(src + k);
+                cost[i][k] = t.x, cost[i][k + 1] = t.y, cost[i][k + 2] = t.z, cost[i][k + 3] = t.w;
+            }
+        } else if (kVec && (C % 2 == 0)) {
+#pragma unroll
+            for (int k = 0; k < C; k += 2) {
+                const float2 t = *reinterpret_cast<const float2 *>(src + k);
+                cost[i][k] = t.x, cost[i][k + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < C; ++k) cost[i][k] = src[k];
+        }
+    }
+    if (NR == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(bin_v);
+        lv[1] = t.x, lv[2] = t.y, lv[3] = t.z, lv[4] = t.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) lv[i + 1] = bin_v[i];
+    }
+    float ov[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        float up_v = __shfl_up_sync(kFullMask, v[C - 1], 1);
+        if (lane0) up_v = lv[i];
+        if (!kExact) {
+#pragma unroll
+            for (int k = 0; k + 1 < C; k += 2) fin = fmaf(cost[i][k], cost[i][k + 1], fin);
+            if (C & 1) fin = fmaf(cost[i][C - 1], 0.0f, fin);
+        }
+#pragma unroll
+        for (int k = C - 1; k >= 0; --k) {
+            const float v_prev = (k == 0) ? up_v : v[k - 1];
+            const float v_cur = v[k];
+            float m;
+            if (kExact)
+                m = (v_cur > v_prev) ? v_cur : v_prev;
+            else
+                m = fmaxf(v_prev, v_cur);
+            float nv = cost[i][k] + m;  // core.pyx:28
+            if (kEdge) nv = (x0 + k <= y + i) ? nv : v_cur;  // above the diagonal the sentinel stays (core.pyx:16-18)
+            v[k] = nv;
+        }
+        ov[i] = v[C - 1];
+        float *dst = vrow + (size_t)i * vpitch;
+        if (C % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < C; k += 4) *reinterpret_cast<float4 *>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        } else if (C % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < C; k += 2) *reinterpret_cast<float2 *>(dst + k) = make_float2(v[k], v[k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < C; ++k) dst[k] = v[k];
+        }
+    }
+    if (lane31) {
+        if (NR == 4) {
+            *reinterpret_cast<float4 *>(bout_v) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) bout_v[i] = ov[i];
+        }
+    }
+    carry_v = lv[NR];
+}
+
+// NR rows of bookkeeping: decisions of rows y .. y+NR-1 from the DP values of rows y-1 .. y+NR-2.
+//   vprev   &vring[x0] (row pitch vpitch, 2R rows): own columns' values;  row r lives in slot r & vmask
+//   lptr / lstride / lmask   where this lane finds the value LEFT of its first column after row r:
+//           lanes >= 1 in the ring (x0 - 1), lane 0 in the boundary ring of the value warp to the left
+template <int C, int NR, bool kEdge>
+__device__ __forceinline__ void k_rows(int (&org)[C], uint32_t (&wl)[C], int bit0, const float *vprev, int vpitch,
+                                       int vmask, const float *lptr, int lstride, int lmask, int &carry_o,
+                                       const int *bin_o, int *bout_o, int y, int x0, bool lane0, bool lane31)
+{
+    float pv[NR][C], left[NR];
+    int lo[NR + 1];
+    lo[0] = carry_o;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const int r = y + i - 1;  // the row whose values decide row y + i
+        const float *src = vprev + (size_t)(r & vmask) * vpitch;
+        if (C % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < C; k += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(src + k);
+                pv[i][k] = t.x, pv[i][k + 1] = t.y, pv[i][k + 2] = t.z, pv[i][k + 3] = t.w;
+            }
+        } else if (C % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < C; k += 2) {
+                const float2 t = *reinterpret_cast<const float2 *>(src + k);
+                pv[i][k] = t.x, pv[i][k + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < C; ++k) pv[i][k] = src[k];
+        }
+        left[i] = lptr[(size_t)(r & lmask) * lstride];
+    }
+    if (NR == 4) {
+        const int4 u = *reinterpret_cast<const int4 *>(bin_o);
+        lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) lo[i + 1] = bin_o[i];
+    }
+    int oo[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
+        if (lane0) up_o = lo[i];
+#pragma unroll
+        for (int k = C - 1; k >= 0; --k) {
+            const float v_prev = (k == 0) ? left[i] : pv[i][k - 1];
+            const float v_cur = pv[i][k];
+            // backtrack rule, core.pyx:32: index == y or value[y-1,x] < value[y-1,x-1]
+            bool diag = v_cur < v_prev;
+            if (kEdge) diag = diag || (x0 + k == y + i);
+            const int o_prev = (k == 0) ? up_o : org[k - 1];
+            int no = diag ? o_prev : org[k];
+            if (kEdge) no = (x0 + k <= y + i) ? no : org[k];
+            org[k] = no;
+            if (diag) wl[k] |= 1u << (bit0 + i);
+        }
+        oo[i] = org[C - 1];
+    }
+    if (lane31) {
+        if (NR == 4) {
+            *reinterpret_cast<int4 *>(bout_o) = make_int4(oo[0], oo[1], oo[2], oo[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) bout_o[i] = oo[i];
+        }
+    }
+    carry_o = lo[NR];
+}
+
 // checkpoint row c_j: c_0 = 0, c_j = 32 j - 1
 __device__ __forceinline__ int check_row(int j) { return j == 0 ? 0 : kCheck * j - 1; }
 
@@ -306,9 +472,8 @@ __device__ __forceinline__ int check_row(int j) { return j == 0 ? 0 : kCheck * j
 // dp_threads(W) consecutive threads (tid counts inside the team) with its own shared-memory region and
 // named barrier `bar`; the standalone kernel runs one team per CTA, the fused kernel up to two.
 __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *smem, int tid, int bar)
-
 {
-    const int nthr = dp_threads(p.W);
+    const int nthr = dp_threads(p.W, p.vk != 0);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
     float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);
     int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
@@ -318,9 +483,9 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
         fence_mbar_init();
     }
     // ring 0 stands in for "the warp left of warp 0": column -1 is the -1e9 sentinel (core.pyx:24)
-    for (int i = tid; i < 2 * p.R; i += nthr) {
-        bnd_v[i] = kNeg;
-        bnd_o[i] = 0;
+    for (int i = tid; i < 4 * p.R; i += nthr) {  // (the value ring is 4R deep with the warp split, else 2R)
+        if (i < (p.vk ? 4 : 2) * p.R) bnd_v[i] = kNeg;
+        if (i < 2 * p.R) bnd_o[i] = 0;
     }
     for (int i = tid; i < kZeroBytes / 16; i += nthr) reinterpret_cast<uint4 *>(zero_s)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();  // zero_s is read by the bulk-store engine
@@ -330,7 +495,7 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
 // Aligns utterance b.  Runs on the dp_threads(W) threads of one team; `slot` selects the team's region of
 // the spill workspace; g_base is the running cost-tile counter of this CTA's stage ring (mbarrier phases
 // continue across utterances).
-template <int C, int R, int W, bool kVec, bool kNoise = false>
+template <int C, int R, int W, bool kVec, bool kNoise = false, bool kVK = false>
 __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
                                         int bar)
 {
@@ -339,8 +504,12 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     const int T = p.T, S = p.S;
     const int t_y = p.t_ys[b], t_x = p.t_xs[b];
     constexpr int S_pad = W * 32 * C;
-    constexpr int kThreads = dp_threads(W);
-    constexpr int kDpWarps = W;
+    static_assert(!(kVK && kNoise), "the warp split has no noise variant");
+    static_assert(!kVK || kVec, "the warp split needs 16-byte cost rows");
+    constexpr int kThreads = dp_threads(W, kVK);
+    constexpr int kDpWarps = W;                       // warps that consume cost tiles
+    constexpr int kProducerWarp = kVK ? 2 * W : W;
+    constexpr int kBRing = (kVK ? 4 : 2) * R;         // depth of the value boundary ring
     const int esize = path_elem_size(p.path_dtype);
     const size_t plane = (size_t)T * S;
     unsigned char *path_b = p.path + (size_t)b * plane * esize;
@@ -394,7 +563,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
 
     if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 0] = globaltimer_ns();
     const int n_chunks = (t_y + R - 1) / R;
-    const int n_steps = n_chunks + kDpWarps - 1;
+    const int n_steps = n_chunks + kDpWarps - 1 + (kVK ? 1 : 0);  // the bookkeeping warps trail by one step
     const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
     const size_t total_bytes = (size_t)p.B * plane * 4;
 
@@ -404,7 +573,16 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     for (int pass = 0; pass < 2; ++pass) {
         const uint32_t g0 = g_base + (uint32_t)pass * n_chunks;  // running tile number: stage = g % stages, parity = (g / stages) & 1
         bool saw_nonfinite = false;
-        if (warp == kDpWarps) {
+        if (kVK) {
+            // "row -1": every column holds the -1e9 sentinel, the cell left of column 0 holds 0 (core.pyx:17-25)
+            float *vlast3 = reinterpret_cast<float *>(smem + p.off_vring) + (size_t)(2 * R + 3) * S_pad;
+            float *kring0 = reinterpret_cast<float *>(smem + p.off_kring0);
+            for (int x = tid; x < S_pad; x += kThreads) vlast3[x] = kNeg;
+            for (int i = tid; i < kBRing; i += kThreads) kring0[i] = (i == kBRing - 1) ? 0.0f : kNeg;
+            for (int w = 1 + tid; w <= W; w += kThreads) bnd_v[(size_t)w * kBRing + kBRing - 1] = kNeg;
+            bar_sync(bar, kThreads);
+        }
+        if (warp == kProducerWarp) {
             // =================== producer warp ===================
             auto issue_tile = [&](int c) {
                 const uint32_t g = g0 + c;
@@ -494,6 +672,167 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             if (p.trace && lane == 0)
                 for (int j = 0; j < 3; ++j) p.trace[40960 + (size_t)b * 16 + 8 + j] = (unsigned long long)pacc[j];
             if (pass == 0 && bulk_ok && lane == 0) bulk_wait_all();  // zeros land before the ones are scattered
+        } else if (kVK && warp < W) {
+            // =================== value warps (warp split) ===================
+            const int w = warp;
+            const int x0 = (w * 32 + lane) * C;
+            const bool lane0 = lane == 0, lane31 = lane == 31;
+            float *vring = reinterpret_cast<float *>(smem + p.off_vring);          // [2R][S_pad]
+            float *vlast = vring + (size_t)2 * R * S_pad;                           // [4][S_pad] last row of a chunk
+            float v[C], fin = 0.0f;
+#pragma unroll
+            for (int k = 0; k < C; ++k) v[k] = kNeg;
+            float carry_v = (w == 0) ? 0.0f : kNeg;  // column -1 before row 0 (core.pyx:22-23)
+            const float *bin_v = bnd_v + (size_t)w * kBRing;
+            float *bout_v = bnd_v + (size_t)(w + 1) * kBRing;
+            const int edge_rows = (w + 1) * 32 * C;
+            uint32_t st = g0 % n_stages, st_par = (g0 / n_stages) & 1u;
+            for (int step = 0; step < n_steps; ++step) {
+                const int c = step - w;
+                if (c >= 0 && c < n_chunks) {
+                    const int row0 = c * R;
+                    const int rows = min(R, t_y - row0);
+                    const float *tile = reinterpret_cast<const float *>(smem + p.off_stage + (size_t)st * p.stage_bytes);
+                    mbar_wait(&full[st], st_par);
+                    const float *trow = tile + (x0 < S ? x0 : S - C);
+                    const bool edge = row0 < edge_rows;
+                    float *vbase = vring + x0;
+                    int r = 0;
+#define MAS_VROWS(NR, EDGE, EXACT)                                                                              \
+    v_rows<C, NR, EDGE, kVec, EXACT>(v, fin, trow + (size_t)r * S, S, carry_v, bin_v + ((row0 + r) & (kBRing - 1)), \
+                                     bout_v + ((row0 + r) & (kBRing - 1)),                                        \
+                                     vbase + (size_t)((row0 + r) & (2 * R - 1)) * S_pad, S_pad, row0 + r, x0, lane0, \
+                                     lane31)
+#define MAS_VLOOP(EDGE, EXACT)                  \
+    _Pragma("unroll 1") for (; r + 4 <= rows; r += 4) MAS_VROWS(4, EDGE, EXACT); \
+    _Pragma("unroll 1") for (; r < rows; ++r) MAS_VROWS(1, EDGE, EXACT);
+                    if (p.debug & 32) {
+                    } else if (pass == 0) {
+                        if (edge) {
+                            MAS_VLOOP(true, false)
+                        } else {
+                            MAS_VLOOP(false, false)
+                        }
+                    } else {
+                        if (edge) {
+                            MAS_VLOOP(true, true)
+                        } else {
+                            MAS_VLOOP(false, true)
+                        }
+                    }
+#undef MAS_VLOOP
+#undef MAS_VROWS
+                    // the chunk's last row once more, where the bookkeeping warp can still read it while this
+                    // warp overwrites the ring slot two chunks later
+                    {
+                        float *dst = vlast + (size_t)(c & 3) * S_pad + x0;
+#pragma unroll
+                        for (int k = 0; k < C; ++k) dst[k] = v[k];
+                    }
+                    if (++st == n_stages) st = 0, st_par ^= 1u;
+                }
+                bar_sync(bar, kThreads);
+            }
+            saw_nonfinite = !(fabsf(fin) <= 3.0e38f);  // NaN or Inf
+        } else if (kVK) {
+            // =================== bookkeeping warps (warp split), one step behind their value warp ===================
+            const int w = warp - W;
+            const int x0 = (w * 32 + lane) * C;
+            const bool lane0 = lane == 0, lane31 = lane == 31;
+            const float *vring = reinterpret_cast<const float *>(smem + p.off_vring);
+            const float *vlast = vring + (size_t)2 * R * S_pad;
+            float *kring0 = reinterpret_cast<float *>(smem + p.off_kring0);       // [4R] left of column 0: 0 before row 0
+            int org[C];
+            uint32_t wl[C], wacc[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                org[k] = x0 + k;
+                wl[k] = 0u;
+                wacc[k] = 0u;
+            }
+            int carry_o = 0;
+            const int *bin_o = bnd_o + (size_t)w * ring;
+            int *bout_o = bnd_o + (size_t)(w + 1) * ring;
+            // where this lane finds the value left of its first column after row r (k_rows)
+            const float *lptr = lane0 ? (w == 0 ? kring0 : bnd_v + (size_t)w * kBRing) : vring + x0 - 1;
+            const int lstride = lane0 ? 1 : S_pad, lmask = lane0 ? kBRing - 1 : 2 * R - 1;
+            const int edge_rows = (w + 1) * 32 * C;
+            for (int step = 0; step < n_steps; ++step) {
+                const int c = step - w - 1;
+                if (c >= 0 && c < n_chunks) {
+                    const int row0 = c * R;
+                    const int rows = min(R, t_y - row0);
+                    const int slot0 = (c & 1) * R;
+                    const bool edge = row0 < edge_rows;
+                    // first row of the chunk: the values of row row0 - 1 come from the last-row copy
+                    const float *vl = vlast + (size_t)((c - 1) & 3) * S_pad + x0;
+                    int r = 0;
+#define MAS_KROWS(NR, EDGE, VP, VM, LP, LS, LM)                                                                  \
+    {                                                                                                           \
+        uint32_t w4[C];                                                                                         \
+        _Pragma("unroll") for (int k = 0; k < C; ++k) w4[k] = 0u;                                               \
+        k_rows<C, NR, EDGE>(org, w4, 0, VP, S_pad, VM, LP, LS, LM, carry_o, bin_o + slot0 + r,                  \
+                            bout_o + slot0 + r, row0 + r, x0, lane0, lane31);                                   \
+        _Pragma("unroll") for (int k = 0; k < C; ++k) wl[k] |= w4[k] << r;                                      \
+    }
+                    // row row0 alone (its operands sit in vlast), then groups of 4 and the tail
+                    if (p.debug & 16) {
+                        r = rows;
+                    } else if (edge) {
+                        MAS_KROWS(1, true, vl, 0, (lane0 ? lptr : vl - 1), (lane0 ? lstride : 0), (lane0 ? lmask : 0));
+                    } else {
+                        MAS_KROWS(1, false, vl, 0, (lane0 ? lptr : vl - 1), (lane0 ? lstride : 0), (lane0 ? lmask : 0));
+                    }
+                    if (!(p.debug & 16)) r = 1;
+                    if (edge) {
+#pragma unroll 1
+                        for (; r < rows && (r & 3); ++r) MAS_KROWS(1, true, vring + x0, 2 * R - 1, lptr, lstride, lmask);
+#pragma unroll 1
+                        for (; r + 4 <= rows; r += 4) MAS_KROWS(4, true, vring + x0, 2 * R - 1, lptr, lstride, lmask);
+#pragma unroll 1
+                        for (; r < rows; ++r) MAS_KROWS(1, true, vring + x0, 2 * R - 1, lptr, lstride, lmask);
+                    } else {
+#pragma unroll 1
+                        for (; r < rows && (r & 3); ++r) MAS_KROWS(1, false, vring + x0, 2 * R - 1, lptr, lstride, lmask);
+#pragma unroll 1
+                        for (; r + 4 <= rows; r += 4) MAS_KROWS(4, false, vring + x0, 2 * R - 1, lptr, lstride, lmask);
+#pragma unroll 1
+                        for (; r < rows; ++r) MAS_KROWS(1, false, vring + x0, 2 * R - 1, lptr, lstride, lmask);
+                    }
+#undef MAS_KROWS
+                    if (c == 0 && w == 0 && lane0) kring0[kBRing - 1] = kNeg;  // "before row 0" is over
+                    // decision words: R < 32 accumulates 32 / R chunks per word
+                    const int end_row = row0 + rows;
+                    const bool word_done = ((end_row & (kCheck - 1)) == 0) || (c == n_chunks - 1);
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        if (R == kCheck)
+                            wacc[k] = wl[k];
+                        else
+                            wacc[k] |= wl[k] << (row0 & (kCheck - 1));
+                        wl[k] = 0u;
+                    }
+                    if (word_done) {
+                        uint32_t *wrow = bits + (size_t)((end_row - 1) >> 5) * S_pad + x0;
+#pragma unroll
+                        for (int k = 0; k < C; ++k) wrow[k] = wacc[k];
+#pragma unroll
+                        for (int k = 0; k < C; ++k) wacc[k] = 0u;
+                    }
+                    if ((end_row & (kCheck - 1)) == 0) {
+                        unsigned char *hrow = hop + (size_t)(end_row / kCheck) * S_pad;
+#pragma unroll
+                        for (int k = 0; k < C; ++k) {
+                            hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                            org[k] = x0 + k;
+                        }
+                        if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
+                    }
+                }
+                bar_sync(bar, kThreads);
+            }
+#pragma unroll
+            for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
         } else {
             // =================== DP warps ===================
             const int w = warp;

@@ -20,7 +20,7 @@ struct FusedParams {
     int n_dp;              // the first n_dp CTAs turn into DP CTAs after their share of the contraction
 };
 
-template <int C, int R, int W, bool kPair>
+template <int C, int R, int W, bool kPair, bool kVK>
 __device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensorMap *tm_z, const CUtensorMap *tm_out,
                                            unsigned char *smem)
 {
@@ -36,30 +36,31 @@ __device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensor
         return;
     }
     // DP CTA j aligns utterances j, j + n_dp, ... on its first dp_threads(W) threads
-    if ((int)threadIdx.x >= dp_threads(W)) return;
+    if ((int)threadIdx.x >= dp_threads(W, kVK)) return;
     const int j = (int)blockIdx.x;
     uint32_t g_base = 0;
     dp_role_init(fp.dp, smem, threadIdx.x, kDpBar);
-    for (int b = j; b < fp.dp.B; b += fp.n_dp) dp_role<C, R, W, true>(fp.dp, smem, b, j, g_base, threadIdx.x, kDpBar);
+    for (int b = j; b < fp.dp.B; b += fp.n_dp)
+        dp_role<C, R, W, true, false, kVK>(fp.dp, smem, b, j, g_base, threadIdx.x, kDpBar);
 }
 
-template <int C, int R, int W>
+template <int C, int R, int W, bool kVK>
 __global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_constant__ FusedParams fp,
                                                                   const __grid_constant__ CUtensorMap tm_z,
                                                                   const __grid_constant__ CUtensorMap tm_out)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    fused_body<C, R, W, false>(fp, &tm_z, &tm_out, smem);
+    fused_body<C, R, W, false, kVK>(fp, &tm_z, &tm_out, smem);
 }
 
 // contraction CTAs in pairs (clusters of 2, n_gemm even); the DP CTAs ignore their cluster
-template <int C, int R, int W>
+template <int C, int R, int W, bool kVK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     mas_fused_pair_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CUtensorMap tm_z,
                           const __grid_constant__ CUtensorMap tm_out)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    fused_body<C, R, W, true>(fp, &tm_z, &tm_out, smem);
+    fused_body<C, R, W, true, kVK>(fp, &tm_z, &tm_out, smem);
 }
 
 static int env_int(const char *name, int dflt)
@@ -171,26 +172,30 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     cfg.attrs = attr;
     cfg.numAttrs = env_int("MAS_FUSED_COOP", 1) ? 1 : 0;
     cudaError_t e = cudaErrorInvalidValue;
-#define MAS_FUSED_CASE(CC, WW)                                                                                   \
-    if (dp.C == CC && dp.p.R == 32 && dp.p.W == WW) {                                                            \
+#define MAS_FUSED_CASE(CC, WW, VK)                                                                               \
+    if (dp.C == CC && dp.p.R == 32 && dp.p.W == WW && (dp.p.vk != 0) == VK) {                                    \
         static thread_local int cfg_dev = -1;                                                                    \
         if (dev != cfg_dev) {                                                                                    \
-            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<CC, 32, WW>,                                      \
+            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<CC, 32, WW, VK>,                                  \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));        \
-            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_pair_kernel<CC, 32, WW>,                                 \
+            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_pair_kernel<CC, 32, WW, VK>,                             \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));        \
             cfg_dev = dev;                                                                                       \
         }                                                                                                        \
-        e = pair ? cudaLaunchKernelEx(&cfg, mas_fused_pair_kernel<CC, 32, WW>, fp, tc.tm_z, tc.tm_out)           \
-                 : cudaLaunchKernelEx(&cfg, mas_fused_kernel<CC, 32, WW>, fp, tc.tm_z, tc.tm_out);               \
+        e = pair ? cudaLaunchKernelEx(&cfg, mas_fused_pair_kernel<CC, 32, WW, VK>, fp, tc.tm_z, tc.tm_out)       \
+                 : cudaLaunchKernelEx(&cfg, mas_fused_kernel<CC, 32, WW, VK>, fp, tc.tm_z, tc.tm_out);           \
     }
-    // S <= 256 (the contraction's limit): C = ceil(S / 64) columns per thread with 2 DP warps, or
-    // ceil(S / 128) with 4 (MAS_DP_WARPS=4)
-    MAS_FUSED_CASE(1, 2)
-    else MAS_FUSED_CASE(2, 2)
-    else MAS_FUSED_CASE(3, 2)
-    else MAS_FUSED_CASE(4, 2)
-    else MAS_FUSED_CASE(2, 4)
+    // S <= 256 (the contraction's limit): C = ceil(S / 64) columns per thread with 2 DP warps (value /
+    // bookkeeping split by default), or ceil(S / 128) with 4 (MAS_DP_WARPS=4)
+    MAS_FUSED_CASE(1, 2, true)
+    else MAS_FUSED_CASE(2, 2, true)
+    else MAS_FUSED_CASE(3, 2, true)
+    else MAS_FUSED_CASE(4, 2, true)
+    else MAS_FUSED_CASE(1, 2, false)
+    else MAS_FUSED_CASE(2, 2, false)
+    else MAS_FUSED_CASE(3, 2, false)
+    else MAS_FUSED_CASE(4, 2, false)
+    else MAS_FUSED_CASE(2, 4, false)
     else return MAS_ERR_UNSUPPORTED_SHAPE;
 #undef MAS_FUSED_CASE
     note_launch();
