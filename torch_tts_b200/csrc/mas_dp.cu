@@ -251,8 +251,8 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
 {
     pl = DpPlan{};
     // value / bookkeeping warp split, EXPERIMENTAL (MAS_DP_VK=1 turns it on): S <= 256 with 16-byte rows, no noise,
-    // everything on chip.  The value warps alone run at ~24 cycles per mel row (2x the single-role warps), but two
-    // bookkeeping warps need ~47, so it is not the default yet.
+    // everything on chip.  The value warps alone run at ~24 cycles per mel row (2x the single-role warps), but the
+    // bookkeeping warps do not keep up yet, so it is not the default.
     bool vk = env_int("MAS_DP_VK", 0) && !with_noise && R == 0 && S <= 256 && S % 4 == 0 &&
               (reinterpret_cast<uintptr_t>(neg_cent) & 15) == 0 && dp_team_warps(S) == 2 && dp_chunk_rows(S) == 32;
     if (vk) vk = dp_make_plan(pl, B, T, S, 0, 0, smem_budget ? smem_budget : (size_t)kSmemBudget, false, true);

@@ -36,7 +36,7 @@ namespace mas {
 // thread has the instruction-level parallelism to hide the max -> add latency, and only every C-th
 // link of the dependency chain pays for a shuffle.  W = 4 serves S > 512.
 constexpr int kMaxDpWarps = 4;
-__host__ __device__ constexpr int dp_threads(int W, bool vk = false) { return ((vk ? 2 * W : W) + 1) * 32; }  // + producer warp
+__host__ __device__ constexpr int dp_threads(int W, bool vk = false) { return ((vk ? 3 * W : W) + 1) * 32; }  // + producer warp
 constexpr int kMaxStages = 8;
 constexpr int kCheck = 32;  // checkpoint interval (rows)
 constexpr int kSmemBudget = 227 * 1024;
@@ -397,7 +397,9 @@ __device__ __forceinline__ void v_rows(float (&v)[C], float &fin, const float *t
 //   vprev   &vring[x0] (row pitch vpitch, 2R rows): own columns' values;  row r lives in slot r & vmask
 //   lptr / lstride / lmask   where this lane finds the value LEFT of its first column after row r:
 //           lanes >= 1 in the ring (x0 - 1), lane 0 in the boundary ring of the value warp to the left
-template <int C, int NR, bool kEdge>
+//   kBits / kOrg   which half of the bookkeeping this warp does: the decision words, or the origins (the
+//           only part with a cross-lane chain); both recompute the one compare per cell
+template <int C, int NR, bool kEdge, bool kBits, bool kOrg>
 __device__ __forceinline__ void k_rows(int (&org)[C], uint32_t (&wl)[C], int bit0, const float *vprev, int vpitch,
                                        int vmask, const float *lptr, int lstride, int lmask, int &carry_o,
                                        const int *bin_o, int *bout_o, int y, int x0, bool lane0, bool lane31)
@@ -427,18 +429,23 @@ __device__ __forceinline__ void k_rows(int (&org)[C], uint32_t (&wl)[C], int bit
         }
         left[i] = lptr[(size_t)(r & lmask) * lstride];
     }
-    if (NR == 4) {
-        const int4 u = *reinterpret_cast<const int4 *>(bin_o);
-        lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
-    } else {
+    if (kOrg) {
+        if (NR == 4) {
+            const int4 u = *reinterpret_cast<const int4 *>(bin_o);
+            lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
+        } else {
 #pragma unroll
-        for (int i = 0; i < NR; ++i) lo[i + 1] = bin_o[i];
+            for (int i = 0; i < NR; ++i) lo[i + 1] = bin_o[i];
+        }
     }
     int oo[NR];
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-        int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
-        if (lane0) up_o = lo[i];
+        int up_o = 0;
+        if (kOrg) {
+            up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
+            if (lane0) up_o = lo[i];
+        }
 #pragma unroll
         for (int k = C - 1; k >= 0; --k) {
             const float v_prev = (k == 0) ? left[i] : pv[i][k - 1];
@@ -446,15 +453,19 @@ __device__ __forceinline__ void k_rows(int (&org)[C], uint32_t (&wl)[C], int bit
             // backtrack rule, core.pyx:32: index == y or value[y-1,x] < value[y-1,x-1]
             bool diag = v_cur < v_prev;
             if (kEdge) diag = diag || (x0 + k == y + i);
-            const int o_prev = (k == 0) ? up_o : org[k - 1];
-            int no = diag ? o_prev : org[k];
-            if (kEdge) no = (x0 + k <= y + i) ? no : org[k];
-            org[k] = no;
-            if (diag) wl[k] |= 1u << (bit0 + i);
+            if (kOrg) {
+                const int o_prev = (k == 0) ? up_o : org[k - 1];
+                int no = diag ? o_prev : org[k];
+                if (kEdge) no = (x0 + k <= y + i) ? no : org[k];
+                org[k] = no;
+            }
+            if (kBits) {
+                if (diag) wl[k] |= 1u << (bit0 + i);
+            }
         }
-        oo[i] = org[C - 1];
+        oo[i] = kOrg ? org[C - 1] : 0;
     }
-    if (lane31) {
+    if (kOrg && lane31) {
         if (NR == 4) {
             *reinterpret_cast<int4 *>(bout_o) = make_int4(oo[0], oo[1], oo[2], oo[3]);
         } else {
@@ -462,7 +473,7 @@ __device__ __forceinline__ void k_rows(int (&org)[C], uint32_t (&wl)[C], int bit
             for (int i = 0; i < NR; ++i) bout_o[i] = oo[i];
         }
     }
-    carry_o = lo[NR];
+    if (kOrg) carry_o = lo[NR];
 }
 
 // checkpoint row c_j: c_0 = 0, c_j = 32 j - 1
@@ -508,7 +519,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     static_assert(!kVK || kVec, "the warp split needs 16-byte cost rows");
     constexpr int kThreads = dp_threads(W, kVK);
     constexpr int kDpWarps = W;                       // warps that consume cost tiles
-    constexpr int kProducerWarp = kVK ? 2 * W : W;
+    constexpr int kProducerWarp = kVK ? 3 * W : W;
     constexpr int kBRing = (kVK ? 4 : 2) * R;         // depth of the value boundary ring
     const int esize = path_elem_size(p.path_dtype);
     const size_t plane = (size_t)T * S;
@@ -736,7 +747,10 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             saw_nonfinite = !(fabsf(fin) <= 3.0e38f);  // NaN or Inf
         } else if (kVK) {
             // =================== bookkeeping warps (warp split), one step behind their value warp ===================
-            const int w = warp - W;
+            // warps [W, 2W): origins, hops, checkpoints (the only bookkeeping with a cross-lane chain);
+            // warps [2W, 3W): decision words.  Each recomputes the one compare per cell from the value ring.
+            const bool is_bits = warp >= 2 * W;
+            const int w = is_bits ? warp - 2 * W : warp - W;
             const int x0 = (w * 32 + lane) * C;
             const bool lane0 = lane == 0, lane31 = lane == 31;
             const float *vring = reinterpret_cast<const float *>(smem + p.off_vring);
@@ -759,80 +773,86 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             const int edge_rows = (w + 1) * 32 * C;
             for (int step = 0; step < n_steps; ++step) {
                 const int c = step - w - 1;
-                if (c >= 0 && c < n_chunks) {
+                if (c >= 0 && c < n_chunks && !(p.debug & 16)) {
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
                     const int slot0 = (c & 1) * R;
                     const bool edge = row0 < edge_rows;
                     // first row of the chunk: the values of row row0 - 1 come from the last-row copy
                     const float *vl = vlast + (size_t)((c - 1) & 3) * S_pad + x0;
+                    const float *lp0 = lane0 ? lptr : vl - 1;
+                    const int ls0 = lane0 ? lstride : 0, lm0 = lane0 ? lmask : 0;
                     int r = 0;
-#define MAS_KROWS(NR, EDGE, VP, VM, LP, LS, LM)                                                                  \
+#define MAS_KROWS(NR, EDGE, BITS, VP, VM, LP, LS, LM)                                                            \
     {                                                                                                           \
         uint32_t w4[C];                                                                                         \
         _Pragma("unroll") for (int k = 0; k < C; ++k) w4[k] = 0u;                                               \
-        k_rows<C, NR, EDGE>(org, w4, 0, VP, S_pad, VM, LP, LS, LM, carry_o, bin_o + slot0 + r,                  \
-                            bout_o + slot0 + r, row0 + r, x0, lane0, lane31);                                   \
-        _Pragma("unroll") for (int k = 0; k < C; ++k) wl[k] |= w4[k] << r;                                      \
+        k_rows<C, NR, EDGE, BITS, !BITS>(org, w4, 0, VP, S_pad, VM, LP, LS, LM, carry_o, bin_o + slot0 + r,     \
+                                         bout_o + slot0 + r, row0 + r, x0, lane0, lane31);                      \
+        if (BITS) {                                                                                             \
+            _Pragma("unroll") for (int k = 0; k < C; ++k) wl[k] |= w4[k] << r;                                  \
+        }                                                                                                       \
     }
                     // row row0 alone (its operands sit in vlast), then groups of 4 and the tail
-                    if (p.debug & 16) {
-                        r = rows;
-                    } else if (edge) {
-                        MAS_KROWS(1, true, vl, 0, (lane0 ? lptr : vl - 1), (lane0 ? lstride : 0), (lane0 ? lmask : 0));
+#define MAS_KCHUNK(EDGE, BITS)                                                                                     \
+    MAS_KROWS(1, EDGE, BITS, vl, 0, lp0, ls0, lm0);                                                                \
+    r = 1;                                                                                                         \
+    _Pragma("unroll 1") for (; r < rows && (r & 3); ++r) MAS_KROWS(1, EDGE, BITS, vring + x0, 2 * R - 1, lptr, lstride, lmask); \
+    _Pragma("unroll 1") for (; r + 4 <= rows; r += 4) MAS_KROWS(4, EDGE, BITS, vring + x0, 2 * R - 1, lptr, lstride, lmask);    \
+    _Pragma("unroll 1") for (; r < rows; ++r) MAS_KROWS(1, EDGE, BITS, vring + x0, 2 * R - 1, lptr, lstride, lmask);
+                    if (is_bits) {
+                        if (edge) {
+                            MAS_KCHUNK(true, true)
+                        } else {
+                            MAS_KCHUNK(false, true)
+                        }
                     } else {
-                        MAS_KROWS(1, false, vl, 0, (lane0 ? lptr : vl - 1), (lane0 ? lstride : 0), (lane0 ? lmask : 0));
+                        if (edge) {
+                            MAS_KCHUNK(true, false)
+                        } else {
+                            MAS_KCHUNK(false, false)
+                        }
                     }
-                    if (!(p.debug & 16)) r = 1;
-                    if (edge) {
-#pragma unroll 1
-                        for (; r < rows && (r & 3); ++r) MAS_KROWS(1, true, vring + x0, 2 * R - 1, lptr, lstride, lmask);
-#pragma unroll 1
-                        for (; r + 4 <= rows; r += 4) MAS_KROWS(4, true, vring + x0, 2 * R - 1, lptr, lstride, lmask);
-#pragma unroll 1
-                        for (; r < rows; ++r) MAS_KROWS(1, true, vring + x0, 2 * R - 1, lptr, lstride, lmask);
-                    } else {
-#pragma unroll 1
-                        for (; r < rows && (r & 3); ++r) MAS_KROWS(1, false, vring + x0, 2 * R - 1, lptr, lstride, lmask);
-#pragma unroll 1
-                        for (; r + 4 <= rows; r += 4) MAS_KROWS(4, false, vring + x0, 2 * R - 1, lptr, lstride, lmask);
-#pragma unroll 1
-                        for (; r < rows; ++r) MAS_KROWS(1, false, vring + x0, 2 * R - 1, lptr, lstride, lmask);
-                    }
+#undef MAS_KCHUNK
 #undef MAS_KROWS
-                    if (c == 0 && w == 0 && lane0) kring0[kBRing - 1] = kNeg;  // "before row 0" is over
-                    // decision words: R < 32 accumulates 32 / R chunks per word
                     const int end_row = row0 + rows;
-                    const bool word_done = ((end_row & (kCheck - 1)) == 0) || (c == n_chunks - 1);
-#pragma unroll
-                    for (int k = 0; k < C; ++k) {
-                        if (R == kCheck)
-                            wacc[k] = wl[k];
-                        else
-                            wacc[k] |= wl[k] << (row0 & (kCheck - 1));
-                        wl[k] = 0u;
-                    }
-                    if (word_done) {
-                        uint32_t *wrow = bits + (size_t)((end_row - 1) >> 5) * S_pad + x0;
-#pragma unroll
-                        for (int k = 0; k < C; ++k) wrow[k] = wacc[k];
-#pragma unroll
-                        for (int k = 0; k < C; ++k) wacc[k] = 0u;
-                    }
-                    if ((end_row & (kCheck - 1)) == 0) {
-                        unsigned char *hrow = hop + (size_t)(end_row / kCheck) * S_pad;
+                    if (is_bits) {
+                        // decision words: R < 32 accumulates 32 / R chunks per word
+                        const bool word_done = ((end_row & (kCheck - 1)) == 0) || (c == n_chunks - 1);
 #pragma unroll
                         for (int k = 0; k < C; ++k) {
-                            hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
-                            org[k] = x0 + k;
+                            if (R == kCheck)
+                                wacc[k] = wl[k];
+                            else
+                                wacc[k] |= wl[k] << (row0 & (kCheck - 1));
+                            wl[k] = 0u;
                         }
-                        if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
+                        if (word_done) {
+                            uint32_t *wrow = bits + (size_t)((end_row - 1) >> 5) * S_pad + x0;
+#pragma unroll
+                            for (int k = 0; k < C; ++k) wrow[k] = wacc[k];
+#pragma unroll
+                            for (int k = 0; k < C; ++k) wacc[k] = 0u;
+                        }
+                    } else {
+                        if (c == 0 && w == 0 && lane0) kring0[kBRing - 1] = kNeg;  // "before row 0" is over
+                        if ((end_row & (kCheck - 1)) == 0) {
+                            unsigned char *hrow = hop + (size_t)(end_row / kCheck) * S_pad;
+#pragma unroll
+                            for (int k = 0; k < C; ++k) {
+                                hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                                org[k] = x0 + k;
+                            }
+                            if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
+                        }
                     }
                 }
                 bar_sync(bar, kThreads);
             }
+            if (!is_bits) {
 #pragma unroll
-            for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
+            }
         } else {
             // =================== DP warps ===================
             const int w = warp;
