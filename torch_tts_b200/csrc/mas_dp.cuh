@@ -698,13 +698,16 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             float *bout_v = bnd_v + (size_t)(w + 1) * kBRing;
             const int edge_rows = (w + 1) * 32 * C;
             uint32_t st = g0 % n_stages, st_par = (g0 / n_stages) & 1u;
+            long long vacc[3] = {0, 0, 0};  // diagnostics: cycles in tile wait, compute, barrier
             for (int step = 0; step < n_steps; ++step) {
                 const int c = step - w;
+                long long e0 = p.trace ? clock64() : 0, e1 = e0, e2 = e0;
                 if (c >= 0 && c < n_chunks) {
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
                     const float *tile = reinterpret_cast<const float *>(smem + p.off_stage + (size_t)st * p.stage_bytes);
                     mbar_wait(&full[st], st_par);
+                    if (p.trace) e1 = clock64();
                     const float *trow = tile + (x0 < S ? x0 : S - C);
                     const bool edge = row0 < edge_rows;
                     float *vbase = vring + x0;
@@ -741,9 +744,16 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         for (int k = 0; k < C; ++k) dst[k] = v[k];
                     }
                     if (++st == n_stages) st = 0, st_par ^= 1u;
+                    if (p.trace) e2 = clock64() + (long long)(__float_as_int(v[0]) & 0);
                 }
                 bar_sync(bar, kThreads);
+                if (p.trace) {
+                    const long long e3 = clock64();
+                    vacc[0] += e1 - e0, vacc[1] += e2 - e1, vacc[2] += e3 - e2;
+                }
             }
+            if (p.trace && lane == 0 && w == 0)
+                for (int j = 0; j < 3; ++j) p.trace[40960 + (size_t)b * 16 + j] = (unsigned long long)vacc[j];
             saw_nonfinite = !(fabsf(fin) <= 3.0e38f);  // NaN or Inf
         } else if (kVK) {
             // =================== bookkeeping warps (warp split), one step behind their value warp ===================
@@ -771,8 +781,11 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             const float *lptr = lane0 ? (w == 0 ? kring0 : bnd_v + (size_t)w * kBRing) : vring + x0 - 1;
             const int lstride = lane0 ? 1 : S_pad, lmask = lane0 ? kBRing - 1 : 2 * R - 1;
             const int edge_rows = (w + 1) * 32 * C;
+            long long kacc[2] = {0, 0};  // diagnostics: cycles in compute, barrier
             for (int step = 0; step < n_steps; ++step) {
                 const int c = step - w - 1;
+                const long long f0 = p.trace ? clock64() : 0;
+                long long f1 = f0;
                 if (c >= 0 && c < n_chunks && !(p.debug & 16)) {
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
@@ -846,9 +859,16 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                             if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
                         }
                     }
+                    if (p.trace) f1 = clock64() + (long long)(org[0] & 0) + (long long)(wacc[0] & 0);
                 }
                 bar_sync(bar, kThreads);
+                if (p.trace) {
+                    const long long f2 = clock64();
+                    kacc[0] += f1 - f0, kacc[1] += f2 - f1;
+                }
             }
+            if (p.trace && lane == 0 && w == 0)
+                for (int j = 0; j < 2; ++j) p.trace[40960 + (size_t)b * 16 + (is_bits ? 6 : 4) + j] = (unsigned long long)kacc[j];
             if (!is_bits) {
 #pragma unroll
                 for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
