@@ -78,7 +78,8 @@ def test_expand_path_roundtrip(cuda_device):
     assert torch.equal(tts.expand_path(idx, S, torch.bfloat16).float(), path)
 
 
-@pytest.mark.parametrize("B,S,T", [(70, 64, 256), (9, 192, 384), (5, 100, 260), (3, 32, 132), (4, 256, 1100), (66, 32, 128)])
+@pytest.mark.parametrize("B,S,T", [(70, 64, 256), (9, 192, 384), (5, 100, 260), (3, 32, 132), (4, 256, 1100), (66, 32, 128),
+                                   (1, 256, 1024), (2, 128, 4096), (150, 16, 64)])
 def test_fused_shapes_and_many_utterances(cuda_device, B, S, T):
     """the one-kernel path beyond config 2: more utterances than DP CTAs (a CTA aligns several in turn),
     C = 1..4 columns per thread, a ragged last mel tile, odd numbers of mel tiles for the CTA pairs."""

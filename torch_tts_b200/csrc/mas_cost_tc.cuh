@@ -554,7 +554,11 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_u[c0 + j];
+                for (int j = 0; j < 32; j += 4) {  // broadcast 128-bit loads of the bias
+                    const float4 b4 = *reinterpret_cast<const float4 *>(bias_u + c0 + j);
+                    v[j] = __uint_as_float(r[j]) + b4.x, v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+                    v[j + 2] = __uint_as_float(r[j + 2]) + b4.z, v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+                }
                 if (kStats) {
                     if (t < p.T) {
 #pragma unroll
