@@ -24,8 +24,7 @@ for name, off, labels in [("DP warp 0", 0, ["tile wait", "compute", "bits/hop", 
     for j, lab in enumerate(labels):
         print(f"   {lab:16s} {tr[:, off + j].mean():9.0f} ({tr[:, off + j].mean() / tot:5.1%})")
 
-if os.environ.get("MAS_DP_VK") == "1":
+if os.environ.get("MAS_DP_VK", "1") == "1":
     print("warp split (per utterance, cycles):")
-    for name, off, labels in [("value warp 0", 0, ["tile wait", "compute", "barrier"]), ("origin warp 0", 4, ["compute", "barrier"]),
-                              ("decision-word warp 0", 6, ["compute", "barrier"])]:
+    for name, off, labels in [("value warp 0", 0, ["tile wait", "compute", "bits", "barrier"]), ("origin warp 0", 4, ["compute", "barrier"])]:
         print("  " + name + ": " + ", ".join(f"{lab} {tr[:, off + j].mean():.0f}" for j, lab in enumerate(labels)))

@@ -38,6 +38,13 @@ mx = max(len(r) for r in rows)
 for j in range(mx):
     col = np.array([r[j] for r in rows if len(r) > j])
     print(f"gemm publication {j}: n={len(col):3d} min {col.min():7.1f} mean {col.mean():7.1f} max {col.max():7.1f}")
+ent = buf[49152:49152 + 148].astype(np.int64); left = buf[49152 + 256:49152 + 256 + 148].astype(np.int64)
+zf = buf[49152 + 512:49152 + 512 + 148].astype(np.int64)
+print("CTA entry (us rel): min %.1f max %.1f" % (rel(ent).min(), rel(ent).max()))
+print("contraction role left: DP CTAs min %.1f mean %.1f max %.1f; others min %.1f mean %.1f max %.1f" % (
+    rel(left[:B]).min(), rel(left[:B]).mean(), rel(left[:B]).max(), rel(left[B:]).min(), rel(left[B:]).mean(), rel(left[B:]).max()))
+if (zf[B:] > 0).all():
+    print("zero-fill role done: min %.1f mean %.1f max %.1f" % (rel(zf[B:]).min(), rel(zf[B:]).mean(), rel(zf[B:]).max()))
 print("DP start  (us rel): min %.1f max %.1f" % (rel(dp[:, 0]).min(), rel(dp[:, 0]).max()))
 for k in range(8):
     a = rel(dp[:, 2 + k])

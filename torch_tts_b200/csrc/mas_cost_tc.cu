@@ -22,6 +22,9 @@ __global__ void __launch_bounds__(kNMax) mas_prior_images_kernel(const float *__
                                                                 float *__restrict__ bias_part, int D, int S, int n_kb,
                                                                 uint32_t *flags_to_clear, int n_flags)
 {
+    // let a programmatic dependent (the fused kernel) start its prologue while this grid runs; it waits for
+    // this grid's completion before it reads anything written here
+    asm volatile("griddepcontrol.launch_dependents;");
     const int kb = blockIdx.x, b = blockIdx.y, nb = blockIdx.z;   // K block, utterance, column block
     const int s_img = threadIdx.x;                                // row of the image
     const int s = nb * kNMax + s_img;                             // text column

@@ -231,6 +231,7 @@ struct TcParams {
     int n_blocks;                  // column blocks of kNMax text columns per utterance (1 for S <= 256)
     int m_tiles;                   // ceil(T / 128)
     int wave;                      // tile order: utterances in groups of `wave`, mel-tile-major inside a group
+    int pdl;                       // launched as a programmatic dependent of the prior-images kernel
     int seq_k, seq_pure0;          // unit schedule: see unit_index() in cost_tc_role (standalone: seq_k huge)
     int z_tma, out_tma;            // tensor maps usable (T % 4 == 0 / S % 4 == 0)
     unsigned long long *trace;     // nullable diagnostics buffer: [cta][64] publication times
@@ -325,6 +326,13 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     if (kPair) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: this grid may have started while the kernel that writes the operand
+    // images, the bias partial sums and the cleared flags was still running; everything above overlapped
+    // with it, everything below reads its output.  (Without such a launch the wait returns at once.)
+    if (p.pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        fence_proxy_async_all();  // the images are read through the async proxy (bulk copies)
+    }
 
     // n-th work unit of this CTA (pair), or -1 when it has none left.  Rounds 0 .. seq_k-1 stride all
     // CTAs (pairs); from round seq_k on only the "pure" contraction CTAs (first >= seq_pure0) continue and
@@ -514,8 +522,8 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         unsigned char *ebuf = smem + Cfg::kOffEpi + wq * 2 * kEpiBufBytes;
         uint32_t nt = 0, nst = 0;
         double ssum = 0.0, ssq = 0.0;
-        // lazily published tile flag (fused kernel): the previous unit's flag goes out once this warp's
-        // stores of it have completed, which is checked after the first store of the next unit
+        // tile flag (fused kernel): goes out once all four warps' stores of the unit have completed
+        // (MAS_TC_DEBUG=64: lazily, checked after the first store of the next unit)
         uint32_t *pend_flag = nullptr;
         uint32_t pend_par = 0;
         auto publish = [&](uint32_t *flag, uint32_t par) {
@@ -609,8 +617,15 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 if (p.flags && mt < p.m_tiles) {
                     uint32_t *flag = p.flags + (size_t)b * p.m_tiles + mt;
                     if (p.out_tma && !(p.debug & 2)) {
-                        pend_flag = flag;  // published after the first store of the next unit (or after the loop)
-                        pend_par = a;
+                        if (p.debug & 64) {
+                            pend_flag = flag;  // experiment: publish after the first store of the next unit
+                            pend_par = a;
+                        } else {
+                            // nothing else to do until the next accumulator fills: wait for the stores to land
+                            // and hand the tile to the DP now rather than one unit later
+                            bulk_wait_all();
+                            publish(flag, a);
+                        }
                     } else {
                         __threadfence();
                         publish(flag, a);

@@ -37,12 +37,11 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     off = align_up(off, 128);
     p.off_stage = (uint32_t)off;
     off += (size_t)stages * p.stage_bytes;
-    p.off_vring = (uint32_t)off;
-    if (vk) off += (size_t)(2 * R + 4) * S_pad * 4;   // values of the last 2R rows + the last rows of 4 chunks
-    p.off_kring0 = (uint32_t)off;
-    if (vk) off += (size_t)4 * R * 4;
+    off = align_up(off, 128);
+    p.off_xch = (uint32_t)off;
+    if (vk) off += (size_t)W * 2 * R * 32 * 4;
     p.off_bnd_v = (uint32_t)off;
-    off += (size_t)(W + 1) * (vk ? 4 : 2) * R * 4;
+    off += (size_t)(W + 1) * 2 * R * 4;
     p.off_bnd_o = (uint32_t)off;
     off += (size_t)(W + 1) * 2 * R * 4;
     p.off_zero = (uint32_t)off;
@@ -250,10 +249,10 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
                bool with_noise)
 {
     pl = DpPlan{};
-    // value / bookkeeping warp split, EXPERIMENTAL (MAS_DP_VK=1 turns it on): S <= 256 with 16-byte rows, no noise,
-    // everything on chip.  The value warps alone run at ~24 cycles per mel row (2x the single-role warps), but the
-    // bookkeeping warps do not keep up yet, so it is not the default.
-    bool vk = env_int("MAS_DP_VK", 0) && !with_noise && R == 0 && S <= 256 && S % 4 == 0 &&
+    // value / origin warp split (MAS_DP_VK=0 turns it off): W value warps run the recursion and leave the decision
+    // words, W origin warps one step behind replay them into origins / hops / checkpoints.  S <= 256 with 16-byte
+    // rows, no noise, everything on chip; other shapes keep the single-role warps.
+    bool vk = env_int("MAS_DP_VK", 1) && !with_noise && R == 0 && S <= 256 && S % 4 == 0 &&
               (reinterpret_cast<uintptr_t>(neg_cent) & 15) == 0 && dp_team_warps(S) == 2 && dp_chunk_rows(S) == 32;
     if (vk) vk = dp_make_plan(pl, B, T, S, 0, 0, smem_budget ? smem_budget : (size_t)kSmemBudget, false, true);
     if (!vk && !dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), R,
@@ -276,6 +275,7 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
     p.flags = nullptr;
     p.flag_tiles = 0;
     p.zero_flags = nullptr;
+    p.zero_queue = nullptr;
     p.trace = trace_buffer();
     p.debug = env_int("MAS_DP_DEBUG", 0);
     p.order = nullptr;

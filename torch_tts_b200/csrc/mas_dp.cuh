@@ -36,7 +36,7 @@ namespace mas {
 // thread has the instruction-level parallelism to hide the max -> add latency, and only every C-th
 // link of the dependency chain pays for a shuffle.  W = 4 serves S > 512.
 constexpr int kMaxDpWarps = 4;
-__host__ __device__ constexpr int dp_threads(int W, bool vk = false) { return ((vk ? 3 * W : W) + 1) * 32; }  // + producer warp
+__host__ __device__ constexpr int dp_threads(int W, bool vk = false) { return ((vk ? 2 * W : W) + 1) * 32; }  // + producer warp
 constexpr int kMaxStages = 8;
 constexpr int kCheck = 32;  // checkpoint interval (rows)
 constexpr int kSmemBudget = 227 * 1024;
@@ -63,6 +63,7 @@ struct DpParams {
     int32_t *status;
     uint32_t *flags;        // nullable: [B][flag_tiles] cost-tile-ready flags of the fused kernel (consumed and reset here)
     int flag_tiles;         // mel tiles of 128 rows per utterance
+    uint32_t *zero_queue;   // fused kernel: work counter of the zero-fill role (cleared with the flags)
     uint32_t *zero_flags;   // nullable: [B] set by whoever zero-fills the path plane of an utterance (fused kernel: the
                             // contraction CTAs, once they run out of tiles); consumed and reset here
     unsigned long long *trace;  // nullable diagnostics buffer: [12288 + utterance * 32]: start, tile acquire times, ends
@@ -71,8 +72,8 @@ struct DpParams {
     int B, T, S;
     int R;       // mel rows per chunk (template parameter of the role; 32, 16 or 8)
     int W;       // DP warps per team (template parameter of the role; 2 or 4)
-    int vk;      // value / bookkeeping warp split (W value warps + W bookkeeping warps + producer)
-    uint32_t off_vring, off_kring0;  // vk: DP values of the last 2R rows [2R][S_pad]; left sentinel ring of column 0
+    int vk;      // value / origin warp split (W value warps + W origin warps + producer)
+    uint32_t off_xch;  // vk: lane-to-lane exchange ring of the value warps [W][2R][32] floats
     int stages;  // cost-tile ring depth (2..kMaxStages)
     int path_dtype;
     int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads,
@@ -127,11 +128,13 @@ __device__ __forceinline__ void store_one(unsigned char *path_b, size_t cell, in
 //           true: the reference's compare-select, bit-for-bit also for NaN/Inf input.
 //   kNoise  the stage also holds the noise tile (nz_off floats behind the cost tile): the cost of a cell is
 //           nc + (sd * noise) * scale, rounded after every operation like the reference (models.py:1241-1247)
+constexpr bool kLeadInRows = true;  // dp_rows without origins: column C-1 runs one row ahead (see there)
 struct DpNoise {
     int nz_off;
     float sd, scale;
 };
-template <int C, int NR, bool kEdge, bool kVec, bool kExact, bool kNoise>
+//   kOrg    false: no origin tracking here (warp split: the origin warps rebuild it from the decision words)
+template <int C, int NR, bool kEdge, bool kVec, bool kExact, bool kNoise, bool kOrg = true>
 __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *trow,
                                         int S, int bit0, float &carry_v, int &carry_o, const float *bin_v,
                                         const int *bin_o, float *bout_v, int *bout_o, int y, int x0, bool lane0,
@@ -188,25 +191,69 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
     }
     if (NR == 4) {
         const float4 t = *reinterpret_cast<const float4 *>(bin_v);
-        const int4 u = *reinterpret_cast<const int4 *>(bin_o);
         lv[1] = t.x, lv[2] = t.y, lv[3] = t.z, lv[4] = t.w;
-        lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
+        if (kOrg) {
+            const int4 u = *reinterpret_cast<const int4 *>(bin_o);
+            lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             lv[i + 1] = bin_v[i];
-            lo[i + 1] = bin_o[i];
+            if (kOrg) lo[i + 1] = bin_o[i];
         }
     }
+    if constexpr (!kOrg && kLeadInRows && NR == 4 && C >= 2) {
+        // Column C-1 one row ahead of columns 0..C-2 (same cells, same arithmetic, other order): the shuffle that
+        // carries row i to the next lane is issued one row before the row that consumes it, so the rows do not
+        // serialise on its latency.
+        auto one = [&](float cost_, float v_prev, float v_cur, int dx, int bit, uint32_t &w) {
+            float mx;
+            if (kExact)
+                mx = (v_cur > v_prev) ? v_cur : v_prev;
+            else
+                mx = fmaxf(v_prev, v_cur);
+            bool diag = v_cur < v_prev;
+            if (kEdge) diag = diag || (dx == 0);
+            float nv = cost_ + mx;
+            if (kEdge) nv = (dx >= 0) ? nv : v_cur;
+            if (diag) w |= 1u << bit;
+            return nv;
+        };
+        const int e0 = y - x0;
+        float up[NR];
+        up[0] = __shfl_up_sync(kFullMask, v[C - 1], 1);
+        float vl = one(cost[0][C - 1], v[C - 2], v[C - 1], e0 - (C - 1), bit0, wl[C - 1]);
+        float ovl[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            ovl[i] = vl;  // column C-1 after row i
+            if (i + 1 < NR) up[i + 1] = __shfl_up_sync(kFullMask, vl, 1);
+            if (!kExact) {
+#pragma unroll
+                for (int k = 0; k + 1 < C; k += 2) fin = fmaf(cost[i][k], cost[i][k + 1], fin);
+                if (C & 1) fin = fmaf(cost[i][C - 1], 0.0f, fin);
+            }
+            const float left = lane0 ? lv[i] : up[i];
+#pragma unroll
+            for (int k = C - 2; k >= 0; --k)
+                v[k] = one(cost[i][k], (k == 0) ? left : v[k - 1], v[k], e0 + i - k, bit0 + i, wl[k]);
+            if (i + 1 < NR) vl = one(cost[i + 1][C - 1], v[C - 2], vl, e0 + i + 1 - (C - 1), bit0 + i + 1, wl[C - 1]);
+        }
+        v[C - 1] = vl;
+        if (lane31) *reinterpret_cast<float4 *>(bout_v) = make_float4(ovl[0], ovl[1], ovl[2], ovl[3]);
+        carry_v = lv[NR];
+    } else {
     float ov[NR];
     int oo[NR];
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
         float up_v = __shfl_up_sync(kFullMask, v[C - 1], 1);
-        int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
+        int up_o = 0;
+        if (kOrg) up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
         if (lane0) {
             up_v = lv[i];
-            up_o = lo[i];
+            if (kOrg) up_o = lo[i];
         }
         if (!kExact) {
             // non-finite detection: a product / multiply-add is NaN or Inf as soon as a factor is
@@ -218,7 +265,7 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
 #pragma unroll
         for (int k = C - 1; k >= 0; --k) {
             const float v_prev = (k == 0) ? up_v : v[k - 1];  // value[y-1, x-1]  (core.pyx:21-27)
-            const int o_prev = (k == 0) ? up_o : org[k - 1];
+            const int o_prev = kOrg ? ((k == 0) ? up_o : org[k - 1]) : 0;
             const float v_cur = v[k];                          // value[y-1, x]    (core.pyx:17-20)
             // Cython's max(v_prev, v_cur) is (v_cur > v_prev) ? v_cur : v_prev; with no NaN in
             // flight that is fmaxf (one FMNMX instead of FSETP -> FSEL on the dependency chain)
@@ -232,37 +279,39 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
             bool diag = v_cur < v_prev;
             if (kEdge) diag = diag || (x0 + k == y + i);
             float nv = cost[i][k] + m;  // core.pyx:28
-            int no = diag ? o_prev : org[k];
+            int no = 0;
+            if (kOrg) no = diag ? o_prev : org[k];
             if (kEdge) {
                 const bool in_band = (x0 + k <= y + i);  // upper band edge, core.pyx:16
                 nv = in_band ? nv : v_cur;
-                no = in_band ? no : org[k];
+                if (kOrg) no = in_band ? no : org[k];
             }
             v[k] = nv;
-            org[k] = no;
+            if (kOrg) org[k] = no;
             if (diag) wl[k] |= 1u << (bit0 + i);
         }
         ov[i] = v[C - 1];
-        oo[i] = org[C - 1];
+        oo[i] = kOrg ? org[C - 1] : 0;
     }
     if (lane31) {
         if (NR == 4) {
             *reinterpret_cast<float4 *>(bout_v) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-            *reinterpret_cast<int4 *>(bout_o) = make_int4(oo[0], oo[1], oo[2], oo[3]);
+            if (kOrg) *reinterpret_cast<int4 *>(bout_o) = make_int4(oo[0], oo[1], oo[2], oo[3]);
         } else {
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 bout_v[i] = ov[i];
-                bout_o[i] = oo[i];
+                if (kOrg) bout_o[i] = oo[i];
             }
         }
     }
     carry_v = lv[NR];
-    carry_o = lo[NR];
+    if (kOrg) carry_o = lo[NR];
+    }
 }
 
 // one chunk (<= R rows) of this warp's columns; bin/bout point at the ring slot of the chunk's first row
-template <int C, int R, bool kEdge, bool kVec, bool kExact, bool kNoise>
+template <int C, int R, bool kEdge, bool kVec, bool kExact, bool kNoise, bool kOrg = true>
 __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *tile,
                                          int S, int rows, int row0, float &carry_v, int &carry_o, const float *bin_v,
                                          const int *bin_o, float *bout_v, int *bout_o, int x0, bool lane0, bool lane31,
@@ -282,9 +331,9 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
         uint32_t w8[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) w8[k] = 0u;
-        dp_rows<C, 4, kEdge, kVec, kExact, kNoise>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
+        dp_rows<C, 4, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
                                            bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31, nz);
-        dp_rows<C, 4, kEdge, kVec, kExact, kNoise>(v, org, fin, w8, trow + (size_t)(r + 4) * S, S, 4, carry_v, carry_o,
+        dp_rows<C, 4, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)(r + 4) * S, S, 4, carry_v, carry_o,
                                            bin_v + r + 4, bin_o + r + 4, bout_v + r + 4, bout_o + r + 4, row0 + r + 4, x0,
                                            lane0, lane31, nz);
 #pragma unroll
@@ -295,7 +344,7 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
         uint32_t w8[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) w8[k] = 0u;
-        dp_rows<C, 1, kEdge, kVec, kExact, kNoise>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
+        dp_rows<C, 1, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
                                            bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31, nz);
 #pragma unroll
         for (int k = 0; k < C; ++k) wl[k] |= w8[k] << r;
@@ -303,169 +352,178 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
 }
 
 // ---------------------------------------------------------------------------
-// value / bookkeeping split (kVK).  A DP warp is latency-bound: one in-order warp per scheduler exposes the
-// shuffle and max -> add latencies whatever else it has to issue.  Here the VALUE warps run only the
-// dependency chain (cost load, shuffle, max, add) and publish every row of DP values to a shared ring;
-// the BOOKKEEPING warps, on the other two schedulers and one chunk behind, turn those values into decision
-// bits, origins and checkpoints.  Both see exactly the operands of the reference's compare (core.pyx:28,32).
+// Forward DP of one chunk with the lane-to-lane hand-over taken off the per-row critical path (value
+// warps of the warp split, no origins).  In dp_rows the shuffle that carries column C-1 to the next lane is
+// issued and consumed within one row, and the rows end up serialised on its latency (~50 of the ~57 cycles
+// per row).  Here
+//   * column C-1 runs ONE ROW AHEAD of columns 0..C-2 -- cell (r+1, C-1) needs only (r, C-1) and (r, C-2),
+//     never the left lane -- and
+//   * the hand-over goes through a shared-memory exchange ring xch[row & (2R-1)][lane] instead of a shuffle:
+//     written in tick r (row r+1), loaded by the right-hand lane in tick r+1, consumed in tick r+2.
+// Every tick is its own basic block (the loop exits sit between the ticks), so the distance survives the
+// scheduler.  Lane 31's column of the ring doubles as the boundary ring towards the next warp; lane 0 reads
+// that of the warp on its left (stride 128 B), or ring 0 of bnd_v for warp 0 (stride 4 B).
+// Same cells, same arithmetic, same decision bits as dp_rows: only the order differs.
+//   xs      this lane's slot of row (row0 & (2R-1)) in its warp's exchange ring
+//   lbase   where this lane finds the value left of its column 0: element [row & (2R-1)] at lbase + that * lstride
 // ---------------------------------------------------------------------------
-// NR rows of the value chain for this thread's C columns; vrow = &vring[slot(row y) * S_pad + x0], advanced
-// by the caller's slot arithmetic (rows of one call never wrap: calls start at multiples of 4 rows).
-template <int C, int NR, bool kEdge, bool kVec, bool kExact>
-__device__ __forceinline__ void v_rows(float (&v)[C], float &fin, const float *trow, int S, float &carry_v,
-                                       const float *bin_v, float *bout_v, float *vrow, int vpitch, int y, int x0,
-                                       bool lane0, bool lane31)
+// EXPERIMENT, off: measured 69 cycles per row against 57 for dp_rows without origins -- the rows no longer wait
+// for a shuffle, but the two loads and the store of every tick share scoreboard slots with those of the
+// neighbouring ticks and the warp now stalls on those.
+constexpr bool kLeadColumn = false;
+template <int C, bool kVec>
+__device__ __forceinline__ void load_cost(float (&c)[C], const float *src)
 {
-    float cost[NR][C];
-    float lv[NR + 1];
-    lv[0] = carry_v;
+    if (kVec && (C % 4 == 0)) {
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        const float *src = trow + (size_t)i * S;
-        if (kVec && (C % 4 == 0)) {
-#pragma unroll
-            for (int k = 0; k < C; k += 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(src + k);
-                cost[i][k] = t.x, cost[i][k + 1] = t.y, cost[i][k + 2] = t.z, cost[i][k + 3] = t.w;
-            }
-        } else if (kVec && (C % 2 == 0)) {
-#pragma unroll
-            for (int k = 0; k < C; k += 2) {
-                const float2 t = *reinterpret_cast<const float2 *>(src + k);
-                cost[i][k] = t.x, cost[i][k + 1] = t.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; ++k) cost[i][k] = src[k];
+        for (int k = 0; k < C; k += 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(src + k);
+            c[k] = t.x, c[k + 1] = t.y, c[k + 2] = t.z, c[k + 3] = t.w;
         }
-    }
-    if (NR == 4) {
-        const float4 t = *reinterpret_cast<const float4 *>(bin_v);
-        lv[1] = t.x, lv[2] = t.y, lv[3] = t.z, lv[4] = t.w;
+    } else if (kVec && (C % 2 == 0)) {
+#pragma unroll
+        for (int k = 0; k < C; k += 2) {
+            const float2 t = *reinterpret_cast<const float2 *>(src + k);
+            c[k] = t.x, c[k + 1] = t.y;
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < NR; ++i) lv[i + 1] = bin_v[i];
+        for (int k = 0; k < C; ++k) c[k] = src[k];
     }
-    float ov[NR];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        float up_v = __shfl_up_sync(kFullMask, v[C - 1], 1);
-        if (lane0) up_v = lv[i];
-        if (!kExact) {
-#pragma unroll
-            for (int k = 0; k + 1 < C; k += 2) fin = fmaf(cost[i][k], cost[i][k + 1], fin);
-            if (C & 1) fin = fmaf(cost[i][C - 1], 0.0f, fin);
-        }
-#pragma unroll
-        for (int k = C - 1; k >= 0; --k) {
-            const float v_prev = (k == 0) ? up_v : v[k - 1];
-            const float v_cur = v[k];
-            float m;
-            if (kExact)
-                m = (v_cur > v_prev) ? v_cur : v_prev;
-            else
-                m = fmaxf(v_prev, v_cur);
-            float nv = cost[i][k] + m;  // core.pyx:28
-            if (kEdge) nv = (x0 + k <= y + i) ? nv : v_cur;  // above the diagonal the sentinel stays (core.pyx:16-18)
-            v[k] = nv;
-        }
-        ov[i] = v[C - 1];
-        float *dst = vrow + (size_t)i * vpitch;
-        if (C % 4 == 0) {
-#pragma unroll
-            for (int k = 0; k < C; k += 4) *reinterpret_cast<float4 *>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-        } else if (C % 2 == 0) {
-#pragma unroll
-            for (int k = 0; k < C; k += 2) *reinterpret_cast<float2 *>(dst + k) = make_float2(v[k], v[k + 1]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; ++k) dst[k] = v[k];
-        }
-    }
-    if (lane31) {
-        if (NR == 4) {
-            *reinterpret_cast<float4 *>(bout_v) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NR; ++i) bout_v[i] = ov[i];
-        }
-    }
-    carry_v = lv[NR];
 }
 
-// NR rows of bookkeeping: decisions of rows y .. y+NR-1 from the DP values of rows y-1 .. y+NR-2.
-//   vprev   &vring[x0] (row pitch vpitch, 2R rows): own columns' values;  row r lives in slot r & vmask
-//   lptr / lstride / lmask   where this lane finds the value LEFT of its first column after row r:
-//           lanes >= 1 in the ring (x0 - 1), lane 0 in the boundary ring of the value warp to the left
-//   kBits / kOrg   which half of the bookkeeping this warp does: the decision words, or the origins (the
-//           only part with a cross-lane chain); both recompute the one compare per cell
-template <int C, int NR, bool kEdge, bool kBits, bool kOrg>
-__device__ __forceinline__ void k_rows(int (&org)[C], uint32_t (&wl)[C], int bit0, const float *vprev, int vpitch,
-                                       int vmask, const float *lptr, int lstride, int lmask, int &carry_o,
-                                       const int *bin_o, int *bout_o, int y, int x0, bool lane0, bool lane31)
+// w += m when value[y-1, x] < value[y-1, x-1] (or the cell sits on the diagonal): one FSETP and one
+// predicated add (the bit is still clear, so adding sets it)
+__device__ __forceinline__ void set_bit_if_less(uint32_t &w, float v_cur, float v_prev, uint32_t m)
 {
-    float pv[NR][C], left[NR];
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(w) : "f"(v_cur), "f"(v_prev), "r"(m));
+}
+__device__ __forceinline__ void set_bit_if_less_or(uint32_t &w, float v_cur, float v_prev, uint32_t m, int dx)
+{
+    asm("{\n\t.reg .pred p, q;\n\tsetp.eq.s32 q, %4, 0;\n\tsetp.lt.or.f32 p, %1, %2, q;\n\t@p add.u32 %0, %0, %3;\n\t}"
+        : "+r"(w)
+        : "f"(v_cur), "f"(v_prev), "r"(m), "r"(dx));
+}
+
+template <int C, int kRing, bool kEdge, bool kVec, bool kExact>
+__device__ __forceinline__ void dp_chunk_lead(float (&v)[C], float &fin, uint32_t (&wl)[C], const float *tile, int S,
+                                              int rows, int row0, float *xs, const unsigned char *lbase, int lstride,
+                                              int x0)
+{
+    static_assert(C >= 2, "column C-1 leads column C-2");
+    const float *cp = tile + (x0 < S ? x0 : S - C);  // (threads past S re-read the last real columns, as dp_chunk)
+    float P[C], Q[C];
+    load_cost<C, kVec>(P, cp);
+    load_cost<C, kVec>(Q, cp + S);  // (rows == 1: a row of the next stage or of the pad, never used)
+    cp += 2 * (size_t)S;
+    // one cell: value[y, x] = cost + max(value[y-1, x], value[y-1, x-1]), its decision bit (core.pyx:17-32)
+    auto cell = [&](float cost, float v_prev, float v_cur, int dx /* y - x */, uint32_t m, uint32_t &w) {
+        float mx;
+        if (kExact)
+            mx = (v_cur > v_prev) ? v_cur : v_prev;
+        else
+            mx = fmaxf(v_prev, v_cur);
+        if (kEdge)
+            set_bit_if_less_or(w, v_cur, v_prev, m, dx);
+        else
+            set_bit_if_less(w, v_cur, v_prev, m);
+        float nv = cost + mx;
+        if (kEdge) nv = (dx >= 0) ? nv : v_cur;  // above the band edge nothing moves (core.pyx:16)
+        return nv;
+    };
+    // prologue: the lead cell of row 0 and the left-hand values of rows 0 and 1
+    const int i0 = row0 & (kRing - 1);
+    const unsigned char *lp = lbase + (size_t)i0 * lstride;  // element of row row0
+    float L0 = *reinterpret_cast<const float *>(lbase + (size_t)((row0 - 1) & (kRing - 1)) * lstride);
+    int e = row0 - x0;  // y - x of column 0 in the current row
+    uint32_t m = 1u;
+    float vl = cell(P[C - 1], v[C - 2], v[C - 1], e - (C - 1), m, wl[C - 1]);
+    *xs = vl;
+    __syncwarp();
+    float L1 = *reinterpret_cast<const float *>(lp);
+    // columns 0..C-2 of row r (cost row c, left-hand value L)
+    auto low = [&](const float (&c)[C], float L) {
+        if (!kExact) {
+#pragma unroll
+            for (int k = 0; k + 1 < C; k += 2) fin = fmaf(c[k], c[k + 1], fin);
+            if (C & 1) fin = fmaf(c[C - 1], 0.0f, fin);
+        }
+#pragma unroll
+        for (int k = C - 2; k >= 0; --k) v[k] = cell(c[k], (k == 0) ? L : v[k - 1], v[k], e - k, m, wl[k]);
+    };
+    // the lead cell of row r+1 and its hand-over, the loads of two ticks later
+    auto lead = [&](float (&cur)[C], const float (&nxt)[C], float &L) {
+        m += m;
+        ++e;
+        vl = cell(nxt[C - 1], v[C - 2], vl, e - (C - 1), m, wl[C - 1]);
+        xs += 32;
+        *xs = vl;
+        // (no __syncwarp here: the warp converged in the prologue and the loop is uniform straight-line code, so
+        // this store and the load below execute warp-wide in program order; a warp barrier per row would split
+        // the tick into two basic blocks and cost ~25 cycles of branch-predicate latency)
+        asm volatile("" ::: "memory");
+        lp += lstride;
+        L = *reinterpret_cast<const float *>(lp);
+        load_cost<C, kVec>(cur, cp);
+        cp += S;
+    };
+    const int last = rows - 1;
+    int r = 0;
+    bool odd = false;
+    if (last > 0) {
+#pragma unroll 1
+        for (;;) {
+            low(P, L0);
+            lead(P, Q, L0);
+            if (++r >= last) {
+                odd = true;
+                break;
+            }
+            low(Q, L1);
+            lead(Q, P, L1);
+            if (++r >= last) break;
+        }
+    }
+    if (odd)
+        low(Q, L1);
+    else
+        low(P, L0);
+    v[C - 1] = vl;
+}
+
+// ---------------------------------------------------------------------------
+// value / origin warp split (kVK): the value warps run dp_rows without origins; the origin warps replay
+// the decision words (bit r of wd[k] = row row0 + r took the diagonal, core.pyx:32) into the origins.
+// Same boundary protocol as dp_rows: bin_o / bout_o slots per row, carry_o across calls.
+// ---------------------------------------------------------------------------
+template <int C, int NR, bool kEdge>
+__device__ __forceinline__ void org_rows(int (&org)[C], const uint32_t (&w8)[C], int bit0, int &carry_o, const int *bin_o,
+                                         int *bout_o, int y, int x0, bool lane0, bool lane31)
+{
     int lo[NR + 1];
     lo[0] = carry_o;
+    if (NR == 4) {
+        const int4 u = *reinterpret_cast<const int4 *>(bin_o);
+        lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        const int r = y + i - 1;  // the row whose values decide row y + i
-        const float *src = vprev + (size_t)(r & vmask) * vpitch;
-        if (C % 4 == 0) {
-#pragma unroll
-            for (int k = 0; k < C; k += 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(src + k);
-                pv[i][k] = t.x, pv[i][k + 1] = t.y, pv[i][k + 2] = t.z, pv[i][k + 3] = t.w;
-            }
-        } else if (C % 2 == 0) {
-#pragma unroll
-            for (int k = 0; k < C; k += 2) {
-                const float2 t = *reinterpret_cast<const float2 *>(src + k);
-                pv[i][k] = t.x, pv[i][k + 1] = t.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; ++k) pv[i][k] = src[k];
-        }
-        left[i] = lptr[(size_t)(r & lmask) * lstride];
-    }
-    if (kOrg) {
-        if (NR == 4) {
-            const int4 u = *reinterpret_cast<const int4 *>(bin_o);
-            lo[1] = u.x, lo[2] = u.y, lo[3] = u.z, lo[4] = u.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < NR; ++i) lo[i + 1] = bin_o[i];
-        }
+        for (int i = 0; i < NR; ++i) lo[i + 1] = bin_o[i];
     }
     int oo[NR];
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-        int up_o = 0;
-        if (kOrg) {
-            up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
-            if (lane0) up_o = lo[i];
-        }
+        int up_o = __shfl_up_sync(kFullMask, org[C - 1], 1);
+        if (lane0) up_o = lo[i];
 #pragma unroll
         for (int k = C - 1; k >= 0; --k) {
-            const float v_prev = (k == 0) ? left[i] : pv[i][k - 1];
-            const float v_cur = pv[i][k];
-            // backtrack rule, core.pyx:32: index == y or value[y-1,x] < value[y-1,x-1]
-            bool diag = v_cur < v_prev;
-            if (kEdge) diag = diag || (x0 + k == y + i);
-            if (kOrg) {
-                const int o_prev = (k == 0) ? up_o : org[k - 1];
-                int no = diag ? o_prev : org[k];
-                if (kEdge) no = (x0 + k <= y + i) ? no : org[k];
-                org[k] = no;
-            }
-            if (kBits) {
-                if (diag) wl[k] |= 1u << (bit0 + i);
-            }
+            const int o_prev = (k == 0) ? up_o : org[k - 1];
+            bool diag = (w8[k] >> (bit0 + i)) & 1u;
+            if (kEdge) diag = diag && (x0 + k <= y + i);  // above the band nothing moves (core.pyx:16)
+            org[k] = diag ? o_prev : org[k];
         }
-        oo[i] = kOrg ? org[C - 1] : 0;
+        oo[i] = org[C - 1];
     }
-    if (kOrg && lane31) {
+    if (lane31) {
         if (NR == 4) {
             *reinterpret_cast<int4 *>(bout_o) = make_int4(oo[0], oo[1], oo[2], oo[3]);
         } else {
@@ -473,7 +531,29 @@ __device__ __forceinline__ void k_rows(int (&org)[C], uint32_t (&wl)[C], int bit
             for (int i = 0; i < NR; ++i) bout_o[i] = oo[i];
         }
     }
-    if (kOrg) carry_o = lo[NR];
+    carry_o = lo[NR];
+}
+
+template <int C, bool kEdge>
+__device__ __forceinline__ void org_chunk(int (&org)[C], const uint32_t (&wd)[C], int rows, int row0, int &carry_o,
+                                          const int *bin_o, int *bout_o, int x0, bool lane0, bool lane31)
+{
+    int r = 0;
+#pragma unroll 1
+    for (; r + 8 <= rows; r += 8) {
+        uint32_t w8[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) w8[k] = wd[k] >> r;
+        org_rows<C, 4, kEdge>(org, w8, 0, carry_o, bin_o + r, bout_o + r, row0 + r, x0, lane0, lane31);
+        org_rows<C, 4, kEdge>(org, w8, 4, carry_o, bin_o + r + 4, bout_o + r + 4, row0 + r + 4, x0, lane0, lane31);
+    }
+#pragma unroll 1
+    for (; r < rows; ++r) {
+        uint32_t w8[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) w8[k] = wd[k] >> r;
+        org_rows<C, 1, kEdge>(org, w8, 0, carry_o, bin_o + r, bout_o + r, row0 + r, x0, lane0, lane31);
+    }
 }
 
 // checkpoint row c_j: c_0 = 0, c_j = 32 j - 1
@@ -494,9 +574,9 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
         fence_mbar_init();
     }
     // ring 0 stands in for "the warp left of warp 0": column -1 is the -1e9 sentinel (core.pyx:24)
-    for (int i = tid; i < 4 * p.R; i += nthr) {  // (the value ring is 4R deep with the warp split, else 2R)
-        if (i < (p.vk ? 4 : 2) * p.R) bnd_v[i] = kNeg;
-        if (i < 2 * p.R) bnd_o[i] = 0;
+    for (int i = tid; i < 2 * p.R; i += nthr) {
+        bnd_v[i] = kNeg;
+        bnd_o[i] = 0;
     }
     for (int i = tid; i < kZeroBytes / 16; i += nthr) reinterpret_cast<uint4 *>(zero_s)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();  // zero_s is read by the bulk-store engine
@@ -515,12 +595,10 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     const int T = p.T, S = p.S;
     const int t_y = p.t_ys[b], t_x = p.t_xs[b];
     constexpr int S_pad = W * 32 * C;
-    static_assert(!(kVK && kNoise), "the warp split has no noise variant");
-    static_assert(!kVK || kVec, "the warp split needs 16-byte cost rows");
+    static_assert(!kVK || R == kCheck, "the warp split replays whole decision words: one chunk = one word");
     constexpr int kThreads = dp_threads(W, kVK);
     constexpr int kDpWarps = W;                       // warps that consume cost tiles
-    constexpr int kProducerWarp = kVK ? 3 * W : W;
-    constexpr int kBRing = (kVK ? 4 : 2) * R;         // depth of the value boundary ring
+    constexpr int kProducerWarp = kVK ? 2 * W : W;
     const int esize = path_elem_size(p.path_dtype);
     const size_t plane = (size_t)T * S;
     unsigned char *path_b = p.path + (size_t)b * plane * esize;
@@ -584,15 +662,6 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     for (int pass = 0; pass < 2; ++pass) {
         const uint32_t g0 = g_base + (uint32_t)pass * n_chunks;  // running tile number: stage = g % stages, parity = (g / stages) & 1
         bool saw_nonfinite = false;
-        if (kVK) {
-            // "row -1": every column holds the -1e9 sentinel, the cell left of column 0 holds 0 (core.pyx:17-25)
-            float *vlast3 = reinterpret_cast<float *>(smem + p.off_vring) + (size_t)(2 * R + 3) * S_pad;
-            float *kring0 = reinterpret_cast<float *>(smem + p.off_kring0);
-            for (int x = tid; x < S_pad; x += kThreads) vlast3[x] = kNeg;
-            for (int i = tid; i < kBRing; i += kThreads) kring0[i] = (i == kBRing - 1) ? 0.0f : kNeg;
-            for (int w = 1 + tid; w <= W; w += kThreads) bnd_v[(size_t)w * kBRing + kBRing - 1] = kNeg;
-            bar_sync(bar, kThreads);
-        }
         if (warp == kProducerWarp) {
             // =================== producer warp ===================
             auto issue_tile = [&](int c) {
@@ -683,103 +752,19 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             if (p.trace && lane == 0)
                 for (int j = 0; j < 3; ++j) p.trace[40960 + (size_t)b * 16 + 8 + j] = (unsigned long long)pacc[j];
             if (pass == 0 && bulk_ok && lane == 0) bulk_wait_all();  // zeros land before the ones are scattered
-        } else if (kVK && warp < W) {
-            // =================== value warps (warp split) ===================
-            const int w = warp;
+        } else if (kVK && warp >= W) {
+            // =================== origin warps (warp split), one step behind their value warp ===================
+            // The value warps leave the decision word of every cell; these warps replay it into the
+            // origin / hop / checkpoint bookkeeping, the other cross-lane chain of the forward pass.
+            const int w = warp - W;
             const int x0 = (w * 32 + lane) * C;
             const bool lane0 = lane == 0, lane31 = lane == 31;
-            float *vring = reinterpret_cast<float *>(smem + p.off_vring);          // [2R][S_pad]
-            float *vlast = vring + (size_t)2 * R * S_pad;                           // [4][S_pad] last row of a chunk
-            float v[C], fin = 0.0f;
-#pragma unroll
-            for (int k = 0; k < C; ++k) v[k] = kNeg;
-            float carry_v = (w == 0) ? 0.0f : kNeg;  // column -1 before row 0 (core.pyx:22-23)
-            const float *bin_v = bnd_v + (size_t)w * kBRing;
-            float *bout_v = bnd_v + (size_t)(w + 1) * kBRing;
-            const int edge_rows = (w + 1) * 32 * C;
-            uint32_t st = g0 % n_stages, st_par = (g0 / n_stages) & 1u;
-            long long vacc[3] = {0, 0, 0};  // diagnostics: cycles in tile wait, compute, barrier
-            for (int step = 0; step < n_steps; ++step) {
-                const int c = step - w;
-                long long e0 = p.trace ? clock64() : 0, e1 = e0, e2 = e0;
-                if (c >= 0 && c < n_chunks) {
-                    const int row0 = c * R;
-                    const int rows = min(R, t_y - row0);
-                    const float *tile = reinterpret_cast<const float *>(smem + p.off_stage + (size_t)st * p.stage_bytes);
-                    mbar_wait(&full[st], st_par);
-                    if (p.trace) e1 = clock64();
-                    const float *trow = tile + (x0 < S ? x0 : S - C);
-                    const bool edge = row0 < edge_rows;
-                    float *vbase = vring + x0;
-                    int r = 0;
-#define MAS_VROWS(NR, EDGE, EXACT)                                                                              \
-    v_rows<C, NR, EDGE, kVec, EXACT>(v, fin, trow + (size_t)r * S, S, carry_v, bin_v + ((row0 + r) & (kBRing - 1)), \
-                                     bout_v + ((row0 + r) & (kBRing - 1)),                                        \
-                                     vbase + (size_t)((row0 + r) & (2 * R - 1)) * S_pad, S_pad, row0 + r, x0, lane0, \
-                                     lane31)
-#define MAS_VLOOP(EDGE, EXACT)                  \
-    _Pragma("unroll 1") for (; r + 4 <= rows; r += 4) MAS_VROWS(4, EDGE, EXACT); \
-    _Pragma("unroll 1") for (; r < rows; ++r) MAS_VROWS(1, EDGE, EXACT);
-                    if (p.debug & 32) {
-                    } else if (pass == 0) {
-                        if (edge) {
-                            MAS_VLOOP(true, false)
-                        } else {
-                            MAS_VLOOP(false, false)
-                        }
-                    } else {
-                        if (edge) {
-                            MAS_VLOOP(true, true)
-                        } else {
-                            MAS_VLOOP(false, true)
-                        }
-                    }
-#undef MAS_VLOOP
-#undef MAS_VROWS
-                    // the chunk's last row once more, where the bookkeeping warp can still read it while this
-                    // warp overwrites the ring slot two chunks later
-                    {
-                        float *dst = vlast + (size_t)(c & 3) * S_pad + x0;
-#pragma unroll
-                        for (int k = 0; k < C; ++k) dst[k] = v[k];
-                    }
-                    if (++st == n_stages) st = 0, st_par ^= 1u;
-                    if (p.trace) e2 = clock64() + (long long)(__float_as_int(v[0]) & 0);
-                }
-                bar_sync(bar, kThreads);
-                if (p.trace) {
-                    const long long e3 = clock64();
-                    vacc[0] += e1 - e0, vacc[1] += e2 - e1, vacc[2] += e3 - e2;
-                }
-            }
-            if (p.trace && lane == 0 && w == 0)
-                for (int j = 0; j < 3; ++j) p.trace[40960 + (size_t)b * 16 + j] = (unsigned long long)vacc[j];
-            saw_nonfinite = !(fabsf(fin) <= 3.0e38f);  // NaN or Inf
-        } else if (kVK) {
-            // =================== bookkeeping warps (warp split), one step behind their value warp ===================
-            // warps [W, 2W): origins, hops, checkpoints (the only bookkeeping with a cross-lane chain);
-            // warps [2W, 3W): decision words.  Each recomputes the one compare per cell from the value ring.
-            const bool is_bits = warp >= 2 * W;
-            const int w = is_bits ? warp - 2 * W : warp - W;
-            const int x0 = (w * 32 + lane) * C;
-            const bool lane0 = lane == 0, lane31 = lane == 31;
-            const float *vring = reinterpret_cast<const float *>(smem + p.off_vring);
-            const float *vlast = vring + (size_t)2 * R * S_pad;
-            float *kring0 = reinterpret_cast<float *>(smem + p.off_kring0);       // [4R] left of column 0: 0 before row 0
             int org[C];
-            uint32_t wl[C], wacc[C];
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-                org[k] = x0 + k;
-                wl[k] = 0u;
-                wacc[k] = 0u;
-            }
+            for (int k = 0; k < C; ++k) org[k] = x0 + k;
             int carry_o = 0;
             const int *bin_o = bnd_o + (size_t)w * ring;
             int *bout_o = bnd_o + (size_t)(w + 1) * ring;
-            // where this lane finds the value left of its first column after row r (k_rows)
-            const float *lptr = lane0 ? (w == 0 ? kring0 : bnd_v + (size_t)w * kBRing) : vring + x0 - 1;
-            const int lstride = lane0 ? 1 : S_pad, lmask = lane0 ? kBRing - 1 : 2 * R - 1;
             const int edge_rows = (w + 1) * 32 * C;
             long long kacc[2] = {0, 0};  // diagnostics: cycles in compute, barrier
             for (int step = 0; step < n_steps; ++step) {
@@ -790,76 +775,25 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
                     const int slot0 = (c & 1) * R;
-                    const bool edge = row0 < edge_rows;
-                    // first row of the chunk: the values of row row0 - 1 come from the last-row copy
-                    const float *vl = vlast + (size_t)((c - 1) & 3) * S_pad + x0;
-                    const float *lp0 = lane0 ? lptr : vl - 1;
-                    const int ls0 = lane0 ? lstride : 0, lm0 = lane0 ? lmask : 0;
-                    int r = 0;
-#define MAS_KROWS(NR, EDGE, BITS, VP, VM, LP, LS, LM)                                                            \
-    {                                                                                                           \
-        uint32_t w4[C];                                                                                         \
-        _Pragma("unroll") for (int k = 0; k < C; ++k) w4[k] = 0u;                                               \
-        k_rows<C, NR, EDGE, BITS, !BITS>(org, w4, 0, VP, S_pad, VM, LP, LS, LM, carry_o, bin_o + slot0 + r,     \
-                                         bout_o + slot0 + r, row0 + r, x0, lane0, lane31);                      \
-        if (BITS) {                                                                                             \
-            _Pragma("unroll") for (int k = 0; k < C; ++k) wl[k] |= w4[k] << r;                                  \
-        }                                                                                                       \
-    }
-                    // row row0 alone (its operands sit in vlast), then groups of 4 and the tail
-#define MAS_KCHUNK(EDGE, BITS)                                                                                     \
-    MAS_KROWS(1, EDGE, BITS, vl, 0, lp0, ls0, lm0);                                                                \
-    r = 1;                                                                                                         \
-    _Pragma("unroll 1") for (; r < rows && (r & 3); ++r) MAS_KROWS(1, EDGE, BITS, vring + x0, 2 * R - 1, lptr, lstride, lmask); \
-    _Pragma("unroll 1") for (; r + 4 <= rows; r += 4) MAS_KROWS(4, EDGE, BITS, vring + x0, 2 * R - 1, lptr, lstride, lmask);    \
-    _Pragma("unroll 1") for (; r < rows; ++r) MAS_KROWS(1, EDGE, BITS, vring + x0, 2 * R - 1, lptr, lstride, lmask);
-                    if (is_bits) {
-                        if (edge) {
-                            MAS_KCHUNK(true, true)
-                        } else {
-                            MAS_KCHUNK(false, true)
-                        }
-                    } else {
-                        if (edge) {
-                            MAS_KCHUNK(true, false)
-                        } else {
-                            MAS_KCHUNK(false, false)
-                        }
-                    }
-#undef MAS_KCHUNK
-#undef MAS_KROWS
+                    const uint32_t *wrow = bits + (size_t)(row0 >> 5) * S_pad + x0;
+                    uint32_t wd[C];
+#pragma unroll
+                    for (int k = 0; k < C; ++k) wd[k] = wrow[k];
+                    if (row0 < edge_rows)
+                        org_chunk<C, true>(org, wd, rows, row0, carry_o, bin_o + slot0, bout_o + slot0, x0, lane0, lane31);
+                    else
+                        org_chunk<C, false>(org, wd, rows, row0, carry_o, bin_o + slot0, bout_o + slot0, x0, lane0, lane31);
                     const int end_row = row0 + rows;
-                    if (is_bits) {
-                        // decision words: R < 32 accumulates 32 / R chunks per word
-                        const bool word_done = ((end_row & (kCheck - 1)) == 0) || (c == n_chunks - 1);
+                    if ((end_row & (kCheck - 1)) == 0) {
+                        unsigned char *hrow = hop + (size_t)(end_row / kCheck) * S_pad;
 #pragma unroll
                         for (int k = 0; k < C; ++k) {
-                            if (R == kCheck)
-                                wacc[k] = wl[k];
-                            else
-                                wacc[k] |= wl[k] << (row0 & (kCheck - 1));
-                            wl[k] = 0u;
+                            hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                            org[k] = x0 + k;
                         }
-                        if (word_done) {
-                            uint32_t *wrow = bits + (size_t)((end_row - 1) >> 5) * S_pad + x0;
-#pragma unroll
-                            for (int k = 0; k < C; ++k) wrow[k] = wacc[k];
-#pragma unroll
-                            for (int k = 0; k < C; ++k) wacc[k] = 0u;
-                        }
-                    } else {
-                        if (c == 0 && w == 0 && lane0) kring0[kBRing - 1] = kNeg;  // "before row 0" is over
-                        if ((end_row & (kCheck - 1)) == 0) {
-                            unsigned char *hrow = hop + (size_t)(end_row / kCheck) * S_pad;
-#pragma unroll
-                            for (int k = 0; k < C; ++k) {
-                                hrow[x0 + k] = (unsigned char)(x0 + k - org[k]);
-                                org[k] = x0 + k;
-                            }
-                            if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
-                        }
+                        if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
                     }
-                    if (p.trace) f1 = clock64() + (long long)(org[0] & 0) + (long long)(wacc[0] & 0);
+                    if (p.trace) f1 = clock64() + (long long)(org[0] & 0);
                 }
                 bar_sync(bar, kThreads);
                 if (p.trace) {
@@ -868,11 +802,9 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                 }
             }
             if (p.trace && lane == 0 && w == 0)
-                for (int j = 0; j < 2; ++j) p.trace[40960 + (size_t)b * 16 + (is_bits ? 6 : 4) + j] = (unsigned long long)kacc[j];
-            if (!is_bits) {
+                for (int j = 0; j < 2; ++j) p.trace[40960 + (size_t)b * 16 + 4 + j] = (unsigned long long)kacc[j];
 #pragma unroll
-                for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
-            }
+            for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
         } else {
             // =================== DP warps ===================
             const int w = warp;
@@ -896,6 +828,15 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             float *bout_v = bnd_v + (size_t)(w + 1) * ring;
             int *bout_o = bnd_o + (size_t)(w + 1) * ring;
             const int edge_rows = (w + 1) * 32 * C;  // rows where a column of this warp is still above the diagonal
+            // warp split: exchange ring [W][2R][32] (dp_chunk_lead); slot 2R-1 stands for "row -1"
+            float *xch_w = reinterpret_cast<float *>(smem + p.off_xch) + (size_t)w * ring * 32 + lane;
+            const unsigned char *lbase = reinterpret_cast<const unsigned char *>(
+                lane0 ? (w == 0 ? bnd_v : xch_w - ring * 32 + 31) : xch_w - 1);
+            const int lstride = (lane0 && w == 0) ? 4 : 128;
+            if (kVK) {
+                xch_w[(ring - 1) * 32] = kNeg;
+                if (w == 0 && lane0) bnd_v[ring - 1] = 0.0f;  // left of column 0 before row 0 (core.pyx:22-23)
+            }
             long long dacc[4] = {0, 0, 0, 0};  // diagnostics: cycles in tile wait, compute, bits/hop, barrier
             uint32_t st = g0 % n_stages, st_par = (g0 / n_stages) & 1u;  // stage / mbarrier parity of chunk 0, then stepped
             for (int step = 0; step < n_steps; ++step) {
@@ -912,9 +853,16 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     if (p.trace) d1 = clock64();
                     const bool edge = row0 < edge_rows;
 #define MAS_CHUNK(EDGE, EXACT)                                                                             \
-    dp_chunk<C, R, EDGE, kVec, EXACT, kNoise>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o,        \
-                                              bin_v + slot0, bin_o + slot0, bout_v + slot0, bout_o + slot0, x0,  \
-                                              lane0, lane31, nzp)
+    do {                                                                                                   \
+        if constexpr (kVK && C >= 2 && !kNoise && kLeadColumn)                                             \
+            dp_chunk_lead<C, ring, EDGE, kVec, EXACT>(v, fin, wl, tile, S, rows, row0,                     \
+                                                      xch_w + (size_t)(row0 & (ring - 1)) * 32, lbase, lstride, x0); \
+        else                                                                                               \
+            dp_chunk<C, R, EDGE, kVec, EXACT, kNoise, !kVK>(v, org, fin, wl, tile, S, rows, row0, carry_v, \
+                                                            carry_o, bin_v + slot0, bin_o + slot0,         \
+                                                            bout_v + slot0, bout_o + slot0, x0, lane0,     \
+                                                            lane31, nzp);                                  \
+    } while (0)
                     if (p.debug & 2) {
                     } else if (pass == 0) {
                         if (edge)
@@ -928,6 +876,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                             MAS_CHUNK(false, true);
                     }
 #undef MAS_CHUNK
+                    if (kVK && c == 0 && w == 0 && lane0) bnd_v[ring - 1] = kNeg;  // "before row 0" is over
                     if (p.trace) d2 = clock64() + (long long)(__float_as_int(v[0]) & 0);
                     // decision words: R < 32 accumulates 32 / R chunks per word
                     const int end_row = row0 + rows;
@@ -959,7 +908,8 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         for (int k = 0; k < C; ++k) wacc[k] = 0u;
                     }
                     // checkpoint after rows 31, 63, ...: remember where each column backtracks to, restart origins
-                    if ((end_row & (kCheck - 1)) == 0) {
+                    // (the origin warps' job with the warp split)
+                    if (!kVK && (end_row & (kCheck - 1)) == 0) {
                         unsigned char *hrow = hop + (size_t)(end_row / kCheck) * S_pad;
 #pragma unroll
                         for (int k = 0; k < C; ++k) {
@@ -981,8 +931,10 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             if (p.trace && lane == 0 && (w == 0 || w == 3))
                 for (int j = 0; j < 4; ++j) p.trace[40960 + (size_t)b * 16 + (w ? 4 : 0) + j] = (unsigned long long)dacc[j];
             // origin of the last row relative to its checkpoint -> hop row 0
+            if (!kVK) {
 #pragma unroll
-            for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
+                for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
+            }
             saw_nonfinite = !(fabsf(fin) <= 3.0e38f);  // NaN or Inf
         }
         if (saw_nonfinite) *nonfinite_s = 1;
@@ -1060,10 +1012,14 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     }
 }
 
-// Zero-fills the dense path planes of utterances first, first + step, ... and raises their zero flag.
-// Runs on a whole CTA that has nothing else left to do (fused kernel); `zbuf` is kZeroFillBuf bytes of
-// shared memory.  The DP role of the utterance's owner waits for the flag before it scatters the ones.
-__device__ __forceinline__ void zero_fill_role(const DpParams &p, unsigned char *zbuf, int first, int step)
+// Zero-fills the dense path planes and raises their zero flags.  Runs on a whole CTA that has nothing else
+// left to do (fused kernel); `zbuf` is kZeroFillBuf bytes of shared memory.  The DP role of the utterance's
+// owner waits for the flag before it scatters the ones.
+// Work item = one of kZeroParts slices of one plane, handed out through the queue counter `p.zero_queue` in
+// plane order, so that a CTA that leaves the contraction early takes more of them than one that leaves late
+// (a static split made every plane wait for the slowest CTA).  Two slices are in flight per CTA: the flag of
+// a slice goes out once the stores of the next one have been issued.
+__device__ __forceinline__ void zero_fill_role(const DpParams &p, unsigned char *zbuf)
 {
     const int tid = threadIdx.x, nthr = blockDim.x;
     for (int i = tid; i < (int)(kZeroFillBuf / 16); i += nthr) reinterpret_cast<uint4 *>(zbuf)[i] = make_uint4(0, 0, 0, 0);
@@ -1071,43 +1027,60 @@ __device__ __forceinline__ void zero_fill_role(const DpParams &p, unsigned char 
     __syncthreads();
     const size_t pbytes = (size_t)p.T * p.S * path_elem_size(p.path_dtype);
     const size_t part_bytes = align_up((pbytes + kZeroParts - 1) / kZeroParts, 512);
-    // work item = one of kZeroParts slices of one utterance's plane, so that all helper CTAs stay busy.
-    // Pass 1 issues every store of this CTA (nothing waits in between), pass 2 raises the flags.
+    const int total = p.B * kZeroParts;
     const bool bulk_ok = ((reinterpret_cast<uintptr_t>(p.path) | pbytes) & 15) == 0;
-    for (int wi = first; wi < p.B * kZeroParts; wi += step) {
-        const int b = wi / kZeroParts, part = wi - b * kZeroParts;
-        unsigned char *path_b = p.path + (size_t)b * pbytes;
-        size_t lo = (size_t)part * part_bytes, hi = lo + part_bytes;
-        if (lo > pbytes) lo = pbytes;
-        if (hi > pbytes) hi = pbytes;
-        if (hi <= lo) continue;
-        if (bulk_ok) {
-            if (tid == 0)
-                for (size_t o = lo; o < hi; o += kZeroFillBuf)
-                    bulk_s2g(path_b + o, zbuf, (uint32_t)min((size_t)kZeroFillBuf, hi - o));
-        } else {
-            const int warp = tid >> 5, n_warps = nthr >> 5;
+    if (bulk_ok) {
+        if (tid != 0) return;
+        int prev = -1;
+        for (;;) {
+            const int wi = (int)atomicAdd(p.zero_queue, 1u);
+            if (wi >= total) break;
+            const int b = wi / kZeroParts, part = wi - b * kZeroParts;
+            unsigned char *path_b = p.path + (size_t)b * pbytes;
+            size_t lo = (size_t)part * part_bytes, hi = lo + part_bytes;
+            if (lo > pbytes) lo = pbytes;
+            if (hi > pbytes) hi = pbytes;
+            for (size_t o = lo; o < hi; o += kZeroFillBuf)
+                bulk_s2g(path_b + o, zbuf, (uint32_t)min((size_t)kZeroFillBuf, hi - o));
+            bulk_commit();
+            if (prev >= 0) {
+                bulk_wait_group<1>();  // everything but the slice just issued has landed
+                fence_proxy_async_all();
+                __threadfence();
+                atomicAdd(p.zero_flags + prev / kZeroParts, 1u);  // the DP waits for all kZeroParts slices
+            }
+            prev = wi;
+        }
+        if (prev >= 0) {
+            bulk_wait_all();
+            fence_proxy_async_all();
+            __threadfence();
+            atomicAdd(p.zero_flags + prev / kZeroParts, 1u);
+        }
+    } else {
+        // planes that are not 16-byte aligned: plain stores by all warps, one slice at a time
+        int *wi_s = reinterpret_cast<int *>(zbuf + kZeroFillBuf - 16);  // (the last bytes of zbuf, zero again afterwards)
+        const int warp = tid >> 5, n_warps = nthr >> 5;
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) *wi_s = (int)atomicAdd(p.zero_queue, 1u);
+            __syncthreads();
+            const int wi = *wi_s;
+            if (wi >= total) break;
+            const int b = wi / kZeroParts, part = wi - b * kZeroParts;
+            unsigned char *path_b = p.path + (size_t)b * pbytes;
+            size_t lo = (size_t)part * part_bytes, hi = lo + part_bytes;
+            if (lo > pbytes) lo = pbytes;
+            if (hi > pbytes) hi = pbytes;
             const size_t seg = align_up((hi - lo + n_warps - 1) / n_warps, 512);
             size_t a = lo + (size_t)warp * seg, e = a + seg;
             if (a > hi) a = hi;
             if (e > hi) e = hi;
             if (e > a) zero_bytes_warp(path_b + a, e - a, tid & 31);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(p.zero_flags + b, 1u);
         }
-    }
-    if (bulk_ok) {
-        if (tid == 0) {
-            bulk_commit();
-            bulk_wait_all();
-            fence_proxy_async_all();
-        }
-    } else {
-        __threadfence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        for (int wi = first; wi < p.B * kZeroParts; wi += step)
-            atomicAdd(p.zero_flags + wi / kZeroParts, 1u);  // the DP waits for all kZeroParts slices
     }
 }
 

@@ -26,13 +26,16 @@ __device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensor
 {
     // every CTA starts in the contraction role; the first n_dp CTAs ("hybrid") leave it after seq_k rounds of
     // units and become the DP CTAs, the others finish the remaining units (unit_index() in cost_tc_role)
+    if (fp.tc.trace && threadIdx.x == 0) fp.tc.trace[49152 + blockIdx.x] = globaltimer_ns();  // CTA entry
     if (kPair)
         cost_tc_role<false, true>(fp.tc, tm_z, tm_out, smem, blockIdx.x >> 1, gridDim.x >> 1);
     else
         cost_tc_role<false, false>(fp.tc, tm_z, tm_out, smem, blockIdx.x, gridDim.x);
+    if (fp.tc.trace && threadIdx.x == 0) fp.tc.trace[49152 + 256 + blockIdx.x] = globaltimer_ns();  // contraction role left
     if ((int)blockIdx.x >= fp.n_dp) {
         // out of tiles: zero-fill the dense path planes while the DP CTAs are still busy
-        if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem, (int)blockIdx.x - fp.n_dp, (int)gridDim.x - fp.n_dp);
+        if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem);
+        if (fp.tc.trace && threadIdx.x == 0) fp.tc.trace[49152 + 512 + blockIdx.x] = globaltimer_ns();  // zero-fill done
         return;
     }
     // DP CTA j aligns utterances j, j + n_dp, ... on its first dp_threads(W) threads
@@ -76,8 +79,8 @@ bool fused_supported(int B, int D, int T, int S)
     return cost_tc_supported(B, D, T, S) && (S % 4 == 0) && (T % 4 == 0) && S <= kNMax;
 }
 
-// tile flags [B][m_tiles] followed by the zero-fill flags [B]
-size_t fused_flags_bytes(int B, int T) { return align_up((size_t)B * ((T + kBM - 1) / kBM + 1) * 4, 256); }
+// tile flags [B][m_tiles], the zero-fill flags [B], the zero-fill queue counter
+size_t fused_flags_bytes(int B, int T) { return align_up(((size_t)B * ((T + kBM - 1) / kBM + 1) + 1) * 4, 256); }
 
 int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const int32_t *t_ys, const int32_t *t_xs,
                  float *neg_cent, bool skip_dead_tiles, void *path_out, int path_dtype, int32_t *dur_out,
@@ -90,7 +93,7 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     const int m_tiles = (T + kBM - 1) / kBM;
     TcPlan tc;
     int rc = cost_tc_prepare(tc, z_p, m_p, logs_p, neg_cent, nullptr, skip_dead_tiles ? t_ys : nullptr, cost_ws,
-                             cost_ws_bytes, B, D, T, S, flags, B * (m_tiles + 1), stream);
+                             cost_ws_bytes, B, D, T, S, flags, B * (m_tiles + 1) + 1, stream);
     if (rc) return rc;
     if (!tc.p.z_tma || !tc.p.out_tma) return MAS_ERR_UNSUPPORTED_SHAPE;
     DpPlan dp;
@@ -157,6 +160,7 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     // the contraction-only CTAs zero-fill the path planes when there are enough of them to do it in time
     const bool offload = env_int("MAS_FUSED_ZERO_OFFLOAD", 1) && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1;
     fp.dp.zero_flags = offload ? flags + (size_t)B * m_tiles : nullptr;
+    fp.dp.zero_queue = flags + (size_t)B * (m_tiles + 1);
     size_t smem = dp.smem_bytes;
     if (smem < kTcSmem) smem = kTcSmem;
     if (smem < kZeroFillBuf) smem = kZeroFillBuf;
@@ -166,11 +170,30 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
+    // Launch attributes.  Cooperative: the DP CTAs spin on flags the other CTAs raise, so all of them must be
+    // resident.  Programmatic stream serialization (MAS_FUSED_PDL=0 turns it off): the grid may start while the
+    // prior-images kernel ahead of it in the stream is still running, and overlaps its prologue (barriers, TMEM,
+    // tensor maps) with that kernel; cost_tc_role waits for it before the first dependent read.  Tried once
+    // outside stream capture; a driver that refuses the combination gets plain launches from then on.
+    static int pdl_state = -1;  // -1 untested, 0 refused, 1 works
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    bool use_pdl = env_int("MAS_FUSED_PDL", 1) && (pdl_state == 1 || (pdl_state < 0 && cap == cudaStreamCaptureStatusNone));
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (env_int("MAS_FUSED_COOP", 1)) {
+        attr[n_attr].id = cudaLaunchAttributeCooperative;
+        attr[n_attr].val.cooperative = 1;
+        ++n_attr;
+    }
+    if (use_pdl) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = env_int("MAS_FUSED_COOP", 1) ? 1 : 0;
+    cfg.numAttrs = n_attr;
+    fp.tc.pdl = 1;  // (the wait is a no-op under a plain launch)
     cudaError_t e = cudaErrorInvalidValue;
 #define MAS_FUSED_CASE(CC, WW, VK)                                                                               \
     if (dp.C == CC && dp.p.R == 32 && dp.p.W == WW && (dp.p.vk != 0) == VK) {                                    \
@@ -187,6 +210,7 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     }
     // S <= 256 (the contraction's limit): C = ceil(S / 64) columns per thread with 2 DP warps (value /
     // bookkeeping split by default), or ceil(S / 128) with 4 (MAS_DP_WARPS=4)
+    for (int attempt = 0; attempt < 2; ++attempt) {
     MAS_FUSED_CASE(1, 2, true)
     else MAS_FUSED_CASE(2, 2, true)
     else MAS_FUSED_CASE(3, 2, true)
@@ -197,6 +221,17 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     else MAS_FUSED_CASE(4, 2, false)
     else MAS_FUSED_CASE(2, 4, false)
     else return MAS_ERR_UNSUPPORTED_SHAPE;
+        if (!use_pdl) break;
+        if (e == cudaSuccess) {
+            pdl_state = 1;
+            break;
+        }
+        if (pdl_state == 1) break;  // worked before: a real error
+        (void)cudaGetLastError();
+        pdl_state = 0;
+        use_pdl = false;
+        cfg.numAttrs = n_attr - 1;  // the programmatic attribute is the last one
+    }
 #undef MAS_FUSED_CASE
     note_launch();
     if (e != cudaSuccess) return note_cuda_error(e, "cudaLaunchKernelEx(mas_fused_kernel)");
