@@ -37,9 +37,6 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     off = align_up(off, 128);
     p.off_stage = (uint32_t)off;
     off += (size_t)stages * p.stage_bytes;
-    off = align_up(off, 128);
-    p.off_xch = (uint32_t)off;
-    if (vk) off += (size_t)W * 2 * R * 32 * 4;
     p.off_bnd_v = (uint32_t)off;
     off += (size_t)(W + 1) * 2 * R * 4;
     p.off_bnd_o = (uint32_t)off;

@@ -73,7 +73,6 @@ struct DpParams {
     int R;       // mel rows per chunk (template parameter of the role; 32, 16 or 8)
     int W;       // DP warps per team (template parameter of the role; 2 or 4)
     int vk;      // value / origin warp split (W value warps + W origin warps + producer)
-    uint32_t off_xch;  // vk: lane-to-lane exchange ring of the value warps [W][2R][32] floats
     int stages;  // cost-tile ring depth (2..kMaxStages)
     int path_dtype;
     int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads,
@@ -128,7 +127,6 @@ __device__ __forceinline__ void store_one(unsigned char *path_b, size_t cell, in
 //           true: the reference's compare-select, bit-for-bit also for NaN/Inf input.
 //   kNoise  the stage also holds the noise tile (nz_off floats behind the cost tile): the cost of a cell is
 //           nc + (sd * noise) * scale, rounded after every operation like the reference (models.py:1241-1247)
-constexpr bool kLeadInRows = true;  // dp_rows without origins: column C-1 runs one row ahead (see there)
 struct DpNoise {
     int nz_off;
     float sd, scale;
@@ -203,47 +201,6 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
             if (kOrg) lo[i + 1] = bin_o[i];
         }
     }
-    if constexpr (!kOrg && kLeadInRows && NR == 4 && C >= 2) {
-        // Column C-1 one row ahead of columns 0..C-2 (same cells, same arithmetic, other order): the shuffle that
-        // carries row i to the next lane is issued one row before the row that consumes it, so the rows do not
-        // serialise on its latency.
-        auto one = [&](float cost_, float v_prev, float v_cur, int dx, int bit, uint32_t &w) {
-            float mx;
-            if (kExact)
-                mx = (v_cur > v_prev) ? v_cur : v_prev;
-            else
-                mx = fmaxf(v_prev, v_cur);
-            bool diag = v_cur < v_prev;
-            if (kEdge) diag = diag || (dx == 0);
-            float nv = cost_ + mx;
-            if (kEdge) nv = (dx >= 0) ? nv : v_cur;
-            if (diag) w |= 1u << bit;
-            return nv;
-        };
-        const int e0 = y - x0;
-        float up[NR];
-        up[0] = __shfl_up_sync(kFullMask, v[C - 1], 1);
-        float vl = one(cost[0][C - 1], v[C - 2], v[C - 1], e0 - (C - 1), bit0, wl[C - 1]);
-        float ovl[NR];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            ovl[i] = vl;  // column C-1 after row i
-            if (i + 1 < NR) up[i + 1] = __shfl_up_sync(kFullMask, vl, 1);
-            if (!kExact) {
-#pragma unroll
-                for (int k = 0; k + 1 < C; k += 2) fin = fmaf(cost[i][k], cost[i][k + 1], fin);
-                if (C & 1) fin = fmaf(cost[i][C - 1], 0.0f, fin);
-            }
-            const float left = lane0 ? lv[i] : up[i];
-#pragma unroll
-            for (int k = C - 2; k >= 0; --k)
-                v[k] = one(cost[i][k], (k == 0) ? left : v[k - 1], v[k], e0 + i - k, bit0 + i, wl[k]);
-            if (i + 1 < NR) vl = one(cost[i + 1][C - 1], v[C - 2], vl, e0 + i + 1 - (C - 1), bit0 + i + 1, wl[C - 1]);
-        }
-        v[C - 1] = vl;
-        if (lane31) *reinterpret_cast<float4 *>(bout_v) = make_float4(ovl[0], ovl[1], ovl[2], ovl[3]);
-        carry_v = lv[NR];
-    } else {
     float ov[NR];
     int oo[NR];
 #pragma unroll
@@ -307,7 +264,6 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
     }
     carry_v = lv[NR];
     if (kOrg) carry_o = lo[NR];
-    }
 }
 
 // one chunk (<= R rows) of this warp's columns; bin/bout point at the ring slot of the chunk's first row
@@ -349,146 +305,6 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
 #pragma unroll
         for (int k = 0; k < C; ++k) wl[k] |= w8[k] << r;
     }
-}
-
-// ---------------------------------------------------------------------------
-// Forward DP of one chunk with the lane-to-lane hand-over taken off the per-row critical path (value
-// warps of the warp split, no origins).  In dp_rows the shuffle that carries column C-1 to the next lane is
-// issued and consumed within one row, and the rows end up serialised on its latency (~50 of the ~57 cycles
-// per row).  Here
-//   * column C-1 runs ONE ROW AHEAD of columns 0..C-2 -- cell (r+1, C-1) needs only (r, C-1) and (r, C-2),
-//     never the left lane -- and
-//   * the hand-over goes through a shared-memory exchange ring xch[row & (2R-1)][lane] instead of a shuffle:
-//     written in tick r (row r+1), loaded by the right-hand lane in tick r+1, consumed in tick r+2.
-// Every tick is its own basic block (the loop exits sit between the ticks), so the distance survives the
-// scheduler.  Lane 31's column of the ring doubles as the boundary ring towards the next warp; lane 0 reads
-// that of the warp on its left (stride 128 B), or ring 0 of bnd_v for warp 0 (stride 4 B).
-// Same cells, same arithmetic, same decision bits as dp_rows: only the order differs.
-//   xs      this lane's slot of row (row0 & (2R-1)) in its warp's exchange ring
-//   lbase   where this lane finds the value left of its column 0: element [row & (2R-1)] at lbase + that * lstride
-// ---------------------------------------------------------------------------
-// EXPERIMENT, off: measured 69 cycles per row against 57 for dp_rows without origins -- the rows no longer wait
-// for a shuffle, but the two loads and the store of every tick share scoreboard slots with those of the
-// neighbouring ticks and the warp now stalls on those.
-constexpr bool kLeadColumn = false;
-template <int C, bool kVec>
-__device__ __forceinline__ void load_cost(float (&c)[C], const float *src)
-{
-    if (kVec && (C % 4 == 0)) {
-#pragma unroll
-        for (int k = 0; k < C; k += 4) {
-            const float4 t = *reinterpret_cast<const float4 *>(src + k);
-            c[k] = t.x, c[k + 1] = t.y, c[k + 2] = t.z, c[k + 3] = t.w;
-        }
-    } else if (kVec && (C % 2 == 0)) {
-#pragma unroll
-        for (int k = 0; k < C; k += 2) {
-            const float2 t = *reinterpret_cast<const float2 *>(src + k);
-            c[k] = t.x, c[k + 1] = t.y;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < C; ++k) c[k] = src[k];
-    }
-}
-
-// w += m when value[y-1, x] < value[y-1, x-1] (or the cell sits on the diagonal): one FSETP and one
-// predicated add (the bit is still clear, so adding sets it)
-__device__ __forceinline__ void set_bit_if_less(uint32_t &w, float v_cur, float v_prev, uint32_t m)
-{
-    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(w) : "f"(v_cur), "f"(v_prev), "r"(m));
-}
-__device__ __forceinline__ void set_bit_if_less_or(uint32_t &w, float v_cur, float v_prev, uint32_t m, int dx)
-{
-    asm("{\n\t.reg .pred p, q;\n\tsetp.eq.s32 q, %4, 0;\n\tsetp.lt.or.f32 p, %1, %2, q;\n\t@p add.u32 %0, %0, %3;\n\t}"
-        : "+r"(w)
-        : "f"(v_cur), "f"(v_prev), "r"(m), "r"(dx));
-}
-
-template <int C, int kRing, bool kEdge, bool kVec, bool kExact>
-__device__ __forceinline__ void dp_chunk_lead(float (&v)[C], float &fin, uint32_t (&wl)[C], const float *tile, int S,
-                                              int rows, int row0, float *xs, const unsigned char *lbase, int lstride,
-                                              int x0)
-{
-    static_assert(C >= 2, "column C-1 leads column C-2");
-    const float *cp = tile + (x0 < S ? x0 : S - C);  // (threads past S re-read the last real columns, as dp_chunk)
-    float P[C], Q[C];
-    load_cost<C, kVec>(P, cp);
-    load_cost<C, kVec>(Q, cp + S);  // (rows == 1: a row of the next stage or of the pad, never used)
-    cp += 2 * (size_t)S;
-    // one cell: value[y, x] = cost + max(value[y-1, x], value[y-1, x-1]), its decision bit (core.pyx:17-32)
-    auto cell = [&](float cost, float v_prev, float v_cur, int dx /* y - x */, uint32_t m, uint32_t &w) {
-        float mx;
-        if (kExact)
-            mx = (v_cur > v_prev) ? v_cur : v_prev;
-        else
-            mx = fmaxf(v_prev, v_cur);
-        if (kEdge)
-            set_bit_if_less_or(w, v_cur, v_prev, m, dx);
-        else
-            set_bit_if_less(w, v_cur, v_prev, m);
-        float nv = cost + mx;
-        if (kEdge) nv = (dx >= 0) ? nv : v_cur;  // above the band edge nothing moves (core.pyx:16)
-        return nv;
-    };
-    // prologue: the lead cell of row 0 and the left-hand values of rows 0 and 1
-    const int i0 = row0 & (kRing - 1);
-    const unsigned char *lp = lbase + (size_t)i0 * lstride;  // element of row row0
-    float L0 = *reinterpret_cast<const float *>(lbase + (size_t)((row0 - 1) & (kRing - 1)) * lstride);
-    int e = row0 - x0;  // y - x of column 0 in the current row
-    uint32_t m = 1u;
-    float vl = cell(P[C - 1], v[C - 2], v[C - 1], e - (C - 1), m, wl[C - 1]);
-    *xs = vl;
-    __syncwarp();
-    float L1 = *reinterpret_cast<const float *>(lp);
-    // columns 0..C-2 of row r (cost row c, left-hand value L)
-    auto low = [&](const float (&c)[C], float L) {
-        if (!kExact) {
-#pragma unroll
-            for (int k = 0; k + 1 < C; k += 2) fin = fmaf(c[k], c[k + 1], fin);
-            if (C & 1) fin = fmaf(c[C - 1], 0.0f, fin);
-        }
-#pragma unroll
-        for (int k = C - 2; k >= 0; --k) v[k] = cell(c[k], (k == 0) ? L : v[k - 1], v[k], e - k, m, wl[k]);
-    };
-    // the lead cell of row r+1 and its hand-over, the loads of two ticks later
-    auto lead = [&](float (&cur)[C], const float (&nxt)[C], float &L) {
-        m += m;
-        ++e;
-        vl = cell(nxt[C - 1], v[C - 2], vl, e - (C - 1), m, wl[C - 1]);
-        xs += 32;
-        *xs = vl;
-        // (no __syncwarp here: the warp converged in the prologue and the loop is uniform straight-line code, so
-        // this store and the load below execute warp-wide in program order; a warp barrier per row would split
-        // the tick into two basic blocks and cost ~25 cycles of branch-predicate latency)
-        asm volatile("" ::: "memory");
-        lp += lstride;
-        L = *reinterpret_cast<const float *>(lp);
-        load_cost<C, kVec>(cur, cp);
-        cp += S;
-    };
-    const int last = rows - 1;
-    int r = 0;
-    bool odd = false;
-    if (last > 0) {
-#pragma unroll 1
-        for (;;) {
-            low(P, L0);
-            lead(P, Q, L0);
-            if (++r >= last) {
-                odd = true;
-                break;
-            }
-            low(Q, L1);
-            lead(Q, P, L1);
-            if (++r >= last) break;
-        }
-    }
-    if (odd)
-        low(Q, L1);
-    else
-        low(P, L0);
-    v[C - 1] = vl;
 }
 
 // ---------------------------------------------------------------------------
@@ -828,15 +644,6 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             float *bout_v = bnd_v + (size_t)(w + 1) * ring;
             int *bout_o = bnd_o + (size_t)(w + 1) * ring;
             const int edge_rows = (w + 1) * 32 * C;  // rows where a column of this warp is still above the diagonal
-            // warp split: exchange ring [W][2R][32] (dp_chunk_lead); slot 2R-1 stands for "row -1"
-            float *xch_w = reinterpret_cast<float *>(smem + p.off_xch) + (size_t)w * ring * 32 + lane;
-            const unsigned char *lbase = reinterpret_cast<const unsigned char *>(
-                lane0 ? (w == 0 ? bnd_v : xch_w - ring * 32 + 31) : xch_w - 1);
-            const int lstride = (lane0 && w == 0) ? 4 : 128;
-            if (kVK) {
-                xch_w[(ring - 1) * 32] = kNeg;
-                if (w == 0 && lane0) bnd_v[ring - 1] = 0.0f;  // left of column 0 before row 0 (core.pyx:22-23)
-            }
             long long dacc[4] = {0, 0, 0, 0};  // diagnostics: cycles in tile wait, compute, bits/hop, barrier
             uint32_t st = g0 % n_stages, st_par = (g0 / n_stages) & 1u;  // stage / mbarrier parity of chunk 0, then stepped
             for (int step = 0; step < n_steps; ++step) {
@@ -853,16 +660,9 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     if (p.trace) d1 = clock64();
                     const bool edge = row0 < edge_rows;
 #define MAS_CHUNK(EDGE, EXACT)                                                                             \
-    do {                                                                                                   \
-        if constexpr (kVK && C >= 2 && !kNoise && kLeadColumn)                                             \
-            dp_chunk_lead<C, ring, EDGE, kVec, EXACT>(v, fin, wl, tile, S, rows, row0,                     \
-                                                      xch_w + (size_t)(row0 & (ring - 1)) * 32, lbase, lstride, x0); \
-        else                                                                                               \
-            dp_chunk<C, R, EDGE, kVec, EXACT, kNoise, !kVK>(v, org, fin, wl, tile, S, rows, row0, carry_v, \
-                                                            carry_o, bin_v + slot0, bin_o + slot0,         \
-                                                            bout_v + slot0, bout_o + slot0, x0, lane0,     \
-                                                            lane31, nzp);                                  \
-    } while (0)
+    dp_chunk<C, R, EDGE, kVec, EXACT, kNoise, !kVK>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o,        \
+                                                    bin_v + slot0, bin_o + slot0, bout_v + slot0, bout_o + slot0, \
+                                                    x0, lane0, lane31, nzp)
                     if (p.debug & 2) {
                     } else if (pass == 0) {
                         if (edge)
@@ -876,7 +676,6 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                             MAS_CHUNK(false, true);
                     }
 #undef MAS_CHUNK
-                    if (kVK && c == 0 && w == 0 && lane0) bnd_v[ring - 1] = kNeg;  // "before row 0" is over
                     if (p.trace) d2 = clock64() + (long long)(__float_as_int(v[0]) & 0);
                     // decision words: R < 32 accumulates 32 / R chunks per word
                     const int end_row = row0 + rows;
