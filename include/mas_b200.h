@@ -141,6 +141,33 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
 int mas_expand_path(const int32_t *idx, void *path_out, int path_dtype,
                     int B, int T, int S, void *stream);
 
+/*
+ * The alignment's first consumers in SynthesizerTrn.forward, from the
+ * compact outputs of the calls above instead of the dense path:
+ *
+ * mas_expand_prior_f32 -- replaces vits2/models.py:1270-1271
+ *     m_p    = torch.matmul(attn.squeeze(1), m_p.transpose(1, 2)).transpose(1, 2)
+ *     logs_p = torch.matmul(attn.squeeze(1), logs_p.transpose(1, 2)).transpose(1, 2)
+ *   m_out[b,d,t] = m_p[b,d,idx[b,t]] (0 where idx[b,t] < 0, i.e. past t_y: the path row is all-zero there).
+ *   m_p / logs_p [B,D,S], idx [B,T] int32, outputs [B,D,T]; logs_p and logs_out may both be NULL.
+ *
+ * mas_expand_prior_backward_f32 -- the gradient of that expansion with respect to m_p / logs_p
+ *   (what autograd derives from the two matmuls): g_m_p[b,d,s] = sum of g_m[b,d,t] over the frames
+ *   aligned to s, i.e. t in [start_s, start_s + dur[b,s]) with start = exclusive prefix sum of dur[b,:].
+ *   Fixed summation order, no atomics.  g_logs / g_logs_p may both be NULL.
+ *
+ * mas_logw_f32 -- replaces models.py:1256 + 1261:  w = attn.sum(2);  logw_ = torch.log(w + 1e-6) * x_mask
+ *   from the int32 durations [B,S] and the text lengths [B]; output [B,S] fp32.
+ */
+int mas_expand_prior_f32(const float *m_p, const float *logs_p, const int32_t *idx,
+                         float *m_out, float *logs_out,
+                         int B, int D, int T, int S, void *stream);
+int mas_expand_prior_backward_f32(const float *g_m, const float *g_logs, const int32_t *dur,
+                                  float *g_m_p, float *g_logs_p,
+                                  int B, int D, int T, int S, void *stream);
+int mas_logw_f32(const int32_t *dur, const int32_t *t_xs, float *logw_out,
+                 int B, int S, void *stream);
+
 /* diagnostics: with MAS_TRACE=1 in the environment the fused kernel records device timestamps
  * (ns, %globaltimer) of tile publications and DP milestones; this copies the first n_words of the
  * trace to the host (synchronises the device).  MAS_ERR_NULL_POINTER when tracing is off. */

@@ -142,6 +142,24 @@ def align_torch(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=No
     return attn, attn.sum(2), nc                                                # :1256
 
 
+def expand_prior_torch(attn, m_p, logs_p):
+    """models.py:1270-1271 as written: the prior statistics carried along the one-hot path (CPU torch;
+    differentiable, so autograd of these two matmuls is the backward oracle as well)."""
+    import torch
+
+    m = torch.matmul(attn.squeeze(1), m_p.transpose(1, 2)).transpose(1, 2)        # :1270
+    l = torch.matmul(attn.squeeze(1), logs_p.transpose(1, 2)).transpose(1, 2)     # :1271
+    return m, l
+
+
+def logw_torch(attn, x_mask):
+    """models.py:1256 + 1261: w = attn.sum(2); logw_ = log(w + 1e-6) * x_mask."""
+    import torch
+
+    w = attn.sum(2)
+    return torch.log(w + 1e-6) * x_mask
+
+
 # --------------------------------------------------------------------------
 # the compiled, unmodified reference kernel (oracle/_ref, built by build_ref.py)
 # --------------------------------------------------------------------------

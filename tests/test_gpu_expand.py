@@ -1,0 +1,70 @@
+"""GPU parity of the alignment's first consumers: the prior expansion of
+models.py:1270-1271 as a gather over the compact idx, its backward as a segmented sum, and logw_
+(models.py:1256, 1261) from the int32 durations.  Checked against the reference expressions run in CPU torch."""
+import numpy as np
+import pytest
+import torch
+
+import torch_tts_b200 as tts
+from oracle import mas_oracle
+from torch_tts_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _aligned(B, S, T, ragged, dev, seed=3, D=24):
+    t_x, t_y = synthetic.ragged_lengths(B, S, T, seed) if ragged else synthetic.full_lengths(B, S, T)
+    z_p, m_p, logs_p, x_mask, y_mask = synthetic.prior_inputs(B, S, T, t_x, t_y, D, seed=seed)
+    attn, w, (idx, dur, status) = tts.align(z_p.to(dev), m_p.to(dev), logs_p.to(dev), x_mask.to(dev), y_mask.to(dev),
+                                            return_compact=True)
+    assert int(status.abs().sum()) == 0
+    return t_x, t_y, m_p, logs_p, x_mask, attn, idx, dur
+
+
+@pytest.mark.parametrize("B,S,T,ragged", [(3, 50, 200, True), (2, 256, 1024, False), (4, 97, 333, True), (1, 7, 9, False)])
+def test_expand_prior_is_the_one_hot_matmul(cuda_device, B, S, T, ragged):
+    t_x, t_y, m_p, logs_p, x_mask, attn, idx, dur = _aligned(B, S, T, ragged, cuda_device)
+    want_m, want_l = mas_oracle.expand_prior_torch(attn.cpu(), m_p, logs_p)
+    got_m, got_l = tts.expand_prior(m_p.to(cuda_device), logs_p.to(cuda_device), idx, dur)
+    # a one-hot row times finite numbers is a selection: exact, not a tolerance
+    assert torch.equal(got_m.cpu(), want_m) and torch.equal(got_l.cpu(), want_l)
+    # rows past t_y are zero
+    for b in range(B):
+        assert float(got_m[b, :, int(t_y[b]):].abs().sum()) == 0.0
+    only_m, none = tts.expand_prior(m_p.to(cuda_device), None, idx, dur)
+    assert none is None and torch.equal(only_m.cpu(), want_m)
+
+
+@pytest.mark.parametrize("B,S,T,ragged", [(3, 50, 200, True), (2, 256, 1024, False), (2, 1000, 1003, False)])
+def test_expand_prior_backward_matches_autograd_of_the_matmuls(cuda_device, B, S, T, ragged):
+    t_x, t_y, m_p, logs_p, x_mask, attn, idx, dur = _aligned(B, S, T, ragged, cuda_device, seed=5, D=8)
+    g = torch.Generator().manual_seed(11)
+    gm, gl = torch.randn((B, 8, T), generator=g), torch.randn((B, 8, T), generator=g)
+    m_ref, l_ref = m_p.clone().requires_grad_(True), logs_p.clone().requires_grad_(True)
+    want_m, want_l = mas_oracle.expand_prior_torch(attn.cpu(), m_ref, l_ref)
+    (want_m * gm).sum().add((want_l * gl).sum()).backward()
+    m_dev = m_p.to(cuda_device).requires_grad_(True)
+    l_dev = logs_p.to(cuda_device).requires_grad_(True)
+    got_m, got_l = tts.expand_prior(m_dev, l_dev, idx, dur)
+    (got_m * gm.to(cuda_device)).sum().add((got_l * gl.to(cuda_device)).sum()).backward()
+    # sums of ~T/S terms in a different order than the GEMM: 1e-5 relative to the gradient scale
+    for got, want in ((m_dev.grad.cpu(), m_ref.grad), (l_dev.grad.cpu(), l_ref.grad)):
+        assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+    # columns past t_x receive nothing
+    for b in range(B):
+        assert float(m_dev.grad[b, :, int(t_x[b]):].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("B,S,T,ragged", [(5, 80, 320, True), (2, 256, 1024, False)])
+def test_logw(cuda_device, B, S, T, ragged):
+    t_x, t_y, m_p, logs_p, x_mask, attn, idx, dur = _aligned(B, S, T, ragged, cuda_device, seed=9, D=8)
+    want = mas_oracle.logw_torch(attn.cpu().float(), x_mask)
+    got = tts.logw(dur, t_x.to(cuda_device)).cpu()
+    assert got.shape == want.shape == (B, 1, S)
+    assert (got - want).abs().max().item() <= 1e-6 * 14.0          # |log| <= 13.8; logf vs torch.log: last-ulp
+    assert torch.equal(got == 0, want == 0)                          # masked columns are (signed) zeros on both sides
+
+
+def test_expand_prior_rejects_cpu_tensors():
+    with pytest.raises(tts._lib.MasError):
+        tts.expand_prior(torch.zeros(1, 2, 3), None, torch.zeros(1, 4, dtype=torch.int32), torch.zeros(1, 3, dtype=torch.int32))

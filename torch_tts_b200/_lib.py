@@ -22,7 +22,8 @@ ABI_SYMBOLS = (
     "mas_maximum_path_workspace_bytes", "mas_maximum_path_f32",
     "mas_neg_cent_workspace_bytes", "mas_neg_cent_f32",
     "mas_fused_align_workspace_bytes", "mas_fused_align_f32",
-    "mas_expand_path", "mas_take_launch_count", "mas_debug_read_trace",
+    "mas_expand_path", "mas_expand_prior_f32", "mas_expand_prior_backward_f32", "mas_logw_f32",
+    "mas_take_launch_count", "mas_debug_read_trace",
 )
 
 PATH_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.int32: 3}
@@ -70,6 +71,12 @@ def lib():
                 L.mas_debug_read_trace.argtypes = [vp, i32]
                 L.mas_expand_path.restype = i32
                 L.mas_expand_path.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+                L.mas_expand_prior_f32.restype = i32
+                L.mas_expand_prior_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+                L.mas_expand_prior_backward_f32.restype = i32
+                L.mas_expand_prior_backward_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+                L.mas_logw_f32.restype = i32
+                L.mas_logw_f32.argtypes = [vp, vp, vp, i32, i32, vp]
                 _lib = L
     return _lib
 

@@ -43,6 +43,12 @@ int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, v
 bool dp_noise_supported(const float *neg_cent, const float *noise, int S);
 int lengths_launch(const float *mask, int32_t *t_ys, int32_t *t_xs, int B, int T, int S, cudaStream_t stream);
 int expand_launch(const int32_t *idx, void *path_out, int path_dtype, int B, int T, int S, cudaStream_t stream);
+// mas_expand.cu
+int expand_prior_launch(const float *m_p, const float *logs_p, const int32_t *idx, float *m_out, float *logs_out, int B,
+                        int D, int T, int S, cudaStream_t stream);
+int expand_prior_backward_launch(const float *g_m, const float *g_logs, const int32_t *dur, float *g_m_p, float *g_logs_p,
+                                 int B, int D, int T, int S, cudaStream_t stream);
+int logw_launch(const int32_t *dur, const int32_t *t_xs, float *out, int B, int S, cudaStream_t stream);
 // mas_cost.cu
 size_t cost_workspace_bytes(int B, int D, int T, int S);
 int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
@@ -220,6 +226,33 @@ int mas_expand_path(const int32_t *idx, void *path_out, int path_dtype, int B, i
     int rc = check_dtype(path_dtype);
     if (rc) return rc;
     return expand_launch(idx, path_out, path_dtype, B, T, S, static_cast<cudaStream_t>(stream));
+}
+
+int mas_expand_prior_f32(const float *m_p, const float *logs_p, const int32_t *idx, float *m_out, float *logs_out, int B,
+                         int D, int T, int S, void *stream)
+{
+    if (!m_p || !idx || !m_out) return MAS_ERR_NULL_POINTER;
+    if ((logs_p == nullptr) != (logs_out == nullptr)) return MAS_ERR_NULL_POINTER;
+    if (B < 1 || D < 1 || T < 1 || S < 1) return MAS_ERR_BAD_SHAPE;
+    if (S > MAS_MAX_TEXT || T > MAS_MAX_MEL) return MAS_ERR_UNSUPPORTED_SHAPE;
+    return expand_prior_launch(m_p, logs_p, idx, m_out, logs_out, B, D, T, S, static_cast<cudaStream_t>(stream));
+}
+
+int mas_expand_prior_backward_f32(const float *g_m, const float *g_logs, const int32_t *dur, float *g_m_p, float *g_logs_p,
+                                  int B, int D, int T, int S, void *stream)
+{
+    if (!g_m || !dur || !g_m_p) return MAS_ERR_NULL_POINTER;
+    if ((g_logs == nullptr) != (g_logs_p == nullptr)) return MAS_ERR_NULL_POINTER;
+    if (B < 1 || D < 1 || T < 1 || S < 1) return MAS_ERR_BAD_SHAPE;
+    if (S > MAS_MAX_TEXT || T > MAS_MAX_MEL) return MAS_ERR_UNSUPPORTED_SHAPE;
+    return expand_prior_backward_launch(g_m, g_logs, dur, g_m_p, g_logs_p, B, D, T, S, static_cast<cudaStream_t>(stream));
+}
+
+int mas_logw_f32(const int32_t *dur, const int32_t *t_xs, float *logw_out, int B, int S, void *stream)
+{
+    if (!dur || !t_xs || !logw_out) return MAS_ERR_NULL_POINTER;
+    if (B < 1 || S < 1) return MAS_ERR_BAD_SHAPE;
+    return logw_launch(dur, t_xs, logw_out, B, S, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
