@@ -568,13 +568,37 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     v[j + 2] = __uint_as_float(r[j + 2]) + b4.z, v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
                 }
                 if (kStats) {
-                    if (t < p.T) {
+                    // noise statistics: sum and sum of squares of every real cell.  Per 32-column block the
+                    // thread works in fp32 around a pivot (its first value of the block), where the squares
+                    // are small and nothing cancels, and folds the block into the fp64 totals with exact
+                    // algebra: sum v = sum d + n c, sum v^2 = sum d^2 + 2 c sum d + n c^2.  (Three fp64
+                    // operations per cell here made the epilogue the slowest role: +22 us per config-2 batch.)
+                    if (t < p.T && s_left > c0) {
+                        const float c = v[0];
+                        float sd = 0.0f, sdd = 0.0f, sd1 = 0.0f, sdd1 = 0.0f;
+                        int n = 32;
+                        if (s_left - c0 >= 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c0 + j < s_left) {
-                                ssum += (double)v[j];
-                                ssq += (double)v[j] * (double)v[j];
+                            for (int j = 0; j < 32; j += 2) {  // two chains
+                                const float d0 = v[j] - c, d1 = v[j + 1] - c;
+                                sd += d0, sd1 += d1;
+                                sdd = fmaf(d0, d0, sdd), sdd1 = fmaf(d1, d1, sdd1);
                             }
+                            sd += sd1, sdd += sdd1;
+                        } else {
+                            n = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < s_left) {
+                                    const float dv = v[j] - c;
+                                    sd += dv;
+                                    sdd = fmaf(dv, dv, sdd);
+                                    ++n;
+                                }
+                        }
+                        const double cd = (double)c, nd = (double)n, sdd64 = (double)sdd, sd64 = (double)sd;
+                        ssum += sd64 + nd * cd;
+                        ssq += sdd64 + 2.0 * cd * sd64 + nd * cd * cd;
                     }
                 }
                 if (p.debug & 2) continue;
