@@ -168,6 +168,16 @@ int mas_expand_prior_backward_f32(const float *g_m, const float *g_logs, const i
 int mas_logw_f32(const int32_t *dur, const int32_t *t_xs, float *logw_out,
                  int B, int S, void *stream);
 
+/*
+ * mas_idx_from_durations_f32 -- inference side, replaces commons.generate_path (vits2/commons.py:130-145, called at
+ * models.py:1310) in compact form: idx_out[b,y] = the text column x with cum[x-1] <= y < cum[x], where cum is the
+ * running sum of durations[b,:] (fp32 holding ceil()ed values, as models.py:1303 makes them), or -1 when
+ * y >= t_ys[b] (t_ys may be NULL: T), x >= t_xs[b], or no column covers y.  mas_expand_path turns idx into the dense
+ * path, mas_expand_prior_f32 does the expansion of models.py:1312-1317.
+ */
+int mas_idx_from_durations_f32(const float *durations, const int32_t *t_xs, const int32_t *t_ys,
+                               int32_t *idx_out, int B, int T, int S, void *stream);
+
 /* diagnostics: with MAS_TRACE=1 in the environment the fused kernel records device timestamps
  * (ns, %globaltimer) of tile publications and DP milestones; this copies the first n_words of the
  * trace to the host (synchronises the device).  MAS_ERR_NULL_POINTER when tracing is off. */

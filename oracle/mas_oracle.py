@@ -160,6 +160,19 @@ def logw_torch(attn, x_mask):
     return torch.log(w + 1e-6) * x_mask
 
 
+def generate_path_torch(duration, mask):
+    """commons.py:130-145 restated (CPU torch): duration [b,1,t_x], mask [b,1,t_y,t_x] -> path [b,1,t_y,t_x]."""
+    import torch
+    import torch.nn.functional as F
+
+    b, _, t_y, t_x = mask.shape
+    cum = torch.cumsum(duration, -1).view(b * t_x)                                        # :138-140
+    path = (torch.arange(t_y, dtype=cum.dtype).unsqueeze(0) < cum.unsqueeze(1)).to(mask.dtype)   # sequence_mask :123-127
+    path = path.view(b, t_x, t_y)
+    path = path - F.pad(path, [0, 0, 1, 0, 0, 0])[:, :-1]                                  # :143
+    return path.unsqueeze(1).transpose(2, 3) * mask                                        # :144
+
+
 # --------------------------------------------------------------------------
 # the compiled, unmodified reference kernel (oracle/_ref, built by build_ref.py)
 # --------------------------------------------------------------------------

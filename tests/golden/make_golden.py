@@ -24,7 +24,11 @@ synth_align.npz   the real SynthesizerTrn.forward (models.py:1197-1290) on CPU
                   maximum_path (:1250), the randn_like draw (:1244) and the
                   attn / w it returns, for mas_noise_scale in {None, 0.01, 0}.
 
-Usage:  python tests/golden/make_golden.py
+consumers.npz     the alignment's consumers: commons.generate_path (commons.py:130-145) on seeded ceil()ed
+                  durations, and the statements of models.py:1256, 1261, 1270-1271 (w, logw_, the two
+                  one-hot matmuls) evaluated on that path.  Inputs and outputs stored in full.
+
+Usage:  python tests/golden/make_golden.py [--only consumers]
 """
 from __future__ import annotations
 
@@ -216,10 +220,39 @@ def gen_synth_align(ma):
     return len(out)
 
 
+def gen_consumers():
+    sys.path.insert(0, REF)
+    commons = importlib.import_module("commons")
+    g = torch.Generator().manual_seed(2024)
+    B, S, T, D = 3, 23, 96, 5
+    t_x = torch.tensor([23, 11, 17])
+    x_mask = (torch.arange(S)[None, :] < t_x[:, None]).float().unsqueeze(1)
+    w_ceil = torch.ceil(torch.rand((B, 1, S), generator=g) * 7.0) * x_mask
+    w_ceil[0, 0, 2] = 0.0
+    y_len = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long().clamp_max(T)          # models.py:1304
+    y_mask = commons.sequence_mask(y_len, T).unsqueeze(1).to(x_mask.dtype)             # :1305
+    attn_mask = torch.unsqueeze(x_mask, 2) * torch.unsqueeze(y_mask, -1)               # :1309
+    attn = commons.generate_path(w_ceil, attn_mask)                                    # :1310
+    m_p = torch.randn((B, D, S), generator=g) * x_mask
+    logs_p = torch.randn((B, D, S), generator=g) * x_mask
+    m_e = torch.matmul(attn.squeeze(1), m_p.transpose(1, 2)).transpose(1, 2)           # :1270 / :1312
+    l_e = torch.matmul(attn.squeeze(1), logs_p.transpose(1, 2)).transpose(1, 2)        # :1271 / :1315
+    w = attn.sum(2)                                                                    # :1256
+    logw_ = torch.log(w + 1e-6) * x_mask                                               # :1261
+    out = {"w_ceil": w_ceil.numpy(), "x_mask": x_mask.numpy(), "attn_mask": attn_mask.numpy(), "t_x": t_x.numpy(),
+           "y_len": y_len.numpy(), "attn": attn.numpy(), "m_p": m_p.numpy(), "logs_p": logs_p.numpy(),
+           "m_expanded": m_e.numpy(), "logs_expanded": l_e.numpy(), "w": w.numpy(), "logw_": logw_.numpy()}
+    np.savez_compressed(os.path.join(HERE, "consumers.npz"), **out)
+    return len(out)
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("/root/reference is absent: golden vectors can only be regenerated in the authoring container")
     torch.set_num_threads(4)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "consumers":
+        print("consumers.npz arrays:", gen_consumers())
+        return
     with tempfile.TemporaryDirectory(prefix="mas_golden_") as tmp:
         ma = build_reference_monotonic_align(tmp)
         # models.py does `import monotonic_align` (models.py:12): make it resolve to the build above
@@ -227,7 +260,8 @@ def main():
         n1 = gen_mas_small(ma)
         n2 = gen_mas_seeded(ma)
         n3 = gen_synth_align(ma)
-    for f in ("mas_small.npz", "mas_seeded.npz", "synth_align.npz"):
+    gen_consumers()
+    for f in ("mas_small.npz", "mas_seeded.npz", "synth_align.npz", "consumers.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
     print("arrays:", n1, n2, n3)
 

@@ -68,3 +68,43 @@ def test_logw(cuda_device, B, S, T, ragged):
 def test_expand_prior_rejects_cpu_tensors():
     with pytest.raises(tts._lib.MasError):
         tts.expand_prior(torch.zeros(1, 2, 3), None, torch.zeros(1, 4, dtype=torch.int32), torch.zeros(1, 3, dtype=torch.int32))
+
+
+@pytest.mark.parametrize("B,S,T", [(3, 40, 300), (2, 256, 1500), (1, 5, 8)])
+def test_generate_path_matches_commons(cuda_device, B, S, T):
+    """Inference: durations -> path (commons.generate_path) and the expansion that follows (models.py:1310-1317)."""
+    g = torch.Generator().manual_seed(S)
+    t_x = torch.randint(max(1, S // 2), S + 1, (B,), generator=g)
+    x_mask = (torch.arange(S)[None, :] < t_x[:, None]).float().unsqueeze(1)                 # [B,1,S]
+    w_ceil = torch.ceil(torch.rand((B, 1, S), generator=g) * (2.0 * T / S)) * x_mask         # some zeros, sum may exceed T
+    w_ceil[0, 0, 1] = 0.0                                                                     # a token without frames
+    y_len = torch.clamp_min(w_ceil.sum([1, 2]), 1).long().clamp_max(T)                        # models.py:1304 (capped: fixed T here)
+    y_mask = (torch.arange(T)[None, :] < y_len[:, None]).float().unsqueeze(1)
+    attn_mask = x_mask.unsqueeze(2) * y_mask.unsqueeze(-1)                                    # [B,1,T,S]
+    want = mas_oracle.generate_path_torch(w_ceil, attn_mask)
+    got = tts.generate_path(w_ceil.to(cuda_device), attn_mask.to(cuda_device))
+    assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    # compact form + expansion == the reference's matmul with that path
+    idx = tts.idx_from_durations(w_ceil.to(cuda_device), t_x.to(cuda_device), T, y_len.to(cuda_device))
+    m_p = torch.randn((B, 6, S), generator=g) * x_mask
+    want_m, _ = mas_oracle.expand_prior_torch(want, m_p, m_p)
+    dur_i = want.squeeze(1).sum(1).int()
+    got_m, _ = tts.expand_prior(m_p.to(cuda_device), None, idx, dur_i.to(cuda_device))
+    assert torch.equal(got_m.cpu(), want_m)
+
+
+def test_consumers_golden_through_the_c_abi(cuda_device):
+    """The reference's own outputs (tests/golden/consumers.npz): generate_path, the expansion and logw_."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "consumers.npz"))
+    dev = cuda_device
+    w_ceil, attn_mask = torch.from_numpy(z["w_ceil"]).to(dev), torch.from_numpy(z["attn_mask"]).to(dev)
+    attn = tts.generate_path(w_ceil, attn_mask)
+    assert np.array_equal(attn.cpu().numpy(), z["attn"])
+    T = attn_mask.shape[2]
+    idx = tts.idx_from_durations(w_ceil, torch.from_numpy(z["t_x"]).to(dev), T, torch.from_numpy(z["y_len"]).to(dev))
+    dur = torch.from_numpy(z["w"]).reshape(z["w"].shape[0], -1).int().to(dev)
+    m_e, l_e = tts.expand_prior(torch.from_numpy(z["m_p"]).to(dev), torch.from_numpy(z["logs_p"]).to(dev), idx, dur)
+    assert np.array_equal(m_e.cpu().numpy(), z["m_expanded"]) and np.array_equal(l_e.cpu().numpy(), z["logs_expanded"])
+    lw = tts.logw(dur, torch.from_numpy(z["t_x"]).to(dev)).cpu().numpy()
+    assert np.abs(lw - z["logw_"]).max() <= 1.4e-5 and np.array_equal(lw == 0, z["logw_"] == 0)

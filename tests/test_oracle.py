@@ -182,3 +182,21 @@ def test_path_invariants():
             v = nc[b, y, :tx].astype(np.float64) + np.maximum(v, prev)
         score = nc[b, np.arange(ty), idx].astype(np.float64).sum()
         assert abs(score - v[tx - 1]) < 1e-6 * abs(score)
+
+
+def test_consumers_golden():
+    """oracle restatements of commons.generate_path and models.py:1256/1261/1270-1271 against the reference's own
+    outputs (tests/golden/consumers.npz, made by make_golden.py from /root/reference)."""
+    z = _npz("consumers.npz")
+    w_ceil, attn_mask, x_mask = (torch.from_numpy(z[k]) for k in ("w_ceil", "attn_mask", "x_mask"))
+    attn = mas_oracle.generate_path_torch(w_ceil, attn_mask)
+    assert np.array_equal(attn.numpy(), z["attn"])
+    m_e, l_e = mas_oracle.expand_prior_torch(attn, torch.from_numpy(z["m_p"]), torch.from_numpy(z["logs_p"]))
+    assert np.array_equal(m_e.numpy(), z["m_expanded"]) and np.array_equal(l_e.numpy(), z["logs_expanded"])
+    assert np.array_equal(mas_oracle.logw_torch(attn, x_mask).numpy(), z["logw_"])
+    # the compact form the kernels use says the same thing: a gather over idx is the one-hot matmul
+    path = attn.squeeze(1).numpy()
+    idx = np.where(path.sum(2) > 0, path.argmax(2), -1)
+    m_p = z["m_p"]
+    gathered = np.where(idx[:, None, :] >= 0, np.take_along_axis(m_p, np.maximum(idx, 0)[:, None, :].repeat(m_p.shape[1], 1), 2), 0)
+    assert np.array_equal(gathered.astype(np.float32), z["m_expanded"])

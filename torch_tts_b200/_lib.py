@@ -23,6 +23,7 @@ ABI_SYMBOLS = (
     "mas_neg_cent_workspace_bytes", "mas_neg_cent_f32",
     "mas_fused_align_workspace_bytes", "mas_fused_align_f32",
     "mas_expand_path", "mas_expand_prior_f32", "mas_expand_prior_backward_f32", "mas_logw_f32",
+    "mas_idx_from_durations_f32",
     "mas_take_launch_count", "mas_debug_read_trace",
 )
 
@@ -77,6 +78,8 @@ def lib():
                 L.mas_expand_prior_backward_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
                 L.mas_logw_f32.restype = i32
                 L.mas_logw_f32.argtypes = [vp, vp, vp, i32, i32, vp]
+                L.mas_idx_from_durations_f32.restype = i32
+                L.mas_idx_from_durations_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
                 _lib = L
     return _lib
 

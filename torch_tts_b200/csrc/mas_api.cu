@@ -49,6 +49,8 @@ int expand_prior_launch(const float *m_p, const float *logs_p, const int32_t *id
 int expand_prior_backward_launch(const float *g_m, const float *g_logs, const int32_t *dur, float *g_m_p, float *g_logs_p,
                                  int B, int D, int T, int S, cudaStream_t stream);
 int logw_launch(const int32_t *dur, const int32_t *t_xs, float *out, int B, int S, cudaStream_t stream);
+int idx_from_durations_launch(const float *dur_f, const int32_t *t_xs, const int32_t *t_ys, int32_t *idx, int B, int T,
+                              int S, cudaStream_t stream);
 // mas_cost.cu
 size_t cost_workspace_bytes(int B, int D, int T, int S);
 int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
@@ -253,6 +255,15 @@ int mas_logw_f32(const int32_t *dur, const int32_t *t_xs, float *logw_out, int B
     if (!dur || !t_xs || !logw_out) return MAS_ERR_NULL_POINTER;
     if (B < 1 || S < 1) return MAS_ERR_BAD_SHAPE;
     return logw_launch(dur, t_xs, logw_out, B, S, static_cast<cudaStream_t>(stream));
+}
+
+int mas_idx_from_durations_f32(const float *durations, const int32_t *t_xs, const int32_t *t_ys, int32_t *idx_out, int B,
+                               int T, int S, void *stream)
+{
+    if (!durations || !t_xs || !idx_out) return MAS_ERR_NULL_POINTER;
+    if (B < 1 || T < 1 || S < 1) return MAS_ERR_BAD_SHAPE;
+    if (S > MAS_MAX_TEXT || T > MAS_MAX_MEL) return MAS_ERR_UNSUPPORTED_SHAPE;
+    return idx_from_durations_launch(durations, t_xs, t_ys, idx_out, B, T, S, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

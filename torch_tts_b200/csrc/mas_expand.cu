@@ -179,6 +179,68 @@ __global__ void mas_logw_kernel(const int32_t *__restrict__ dur, const int32_t *
     out[i] = __fmul_rn(logf(__fadd_rn(w, 1e-6f)), mask);
 }
 
+// inference side (commons.generate_path, commons.py:130-145): durations -> alignment.
+// The reference builds the dense path as sequence_mask(cumsum(duration)) minus its copy shifted by one column,
+// times the mask: cell (y, x) is 1 iff cum[x-1] <= y < cum[x], x < t_x, y < t_y.  Here: the compact form
+// idx[b, y] = that x (or -1), from an integer prefix sum (the durations are ceil()ed floats, exact in fp32 and in
+// int32) and a binary search per frame; mas_expand_path / mas_expand_prior_f32 take it from there.
+// One CTA per utterance.
+__global__ void __launch_bounds__(kScatterThreads) mas_idx_from_durations_kernel(const float *__restrict__ dur_f,
+                                                                                 const int32_t *__restrict__ t_xs,
+                                                                                 const int32_t *__restrict__ t_ys,
+                                                                                 int32_t *__restrict__ idx, int T, int S)
+{
+    __shared__ int cum_s[MAS_MAX_TEXT];
+    __shared__ int warp_tot[kScatterThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t_x = min(max(t_xs[b], 0), S);
+    const int per = (S + kScatterThreads - 1) / kScatterThreads;
+    int local = 0;
+    for (int j = 0; j < per; ++j) {
+        const int s = tid * per + j;
+        if (s < S) local += max((int)dur_f[(size_t)b * S + s], 0);
+    }
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int run = incl - local;
+    for (int w = 0; w < warp; ++w) run += warp_tot[w];
+    for (int j = 0; j < per; ++j) {
+        const int s = tid * per + j;
+        if (s < S) {
+            run += max((int)dur_f[(size_t)b * S + s], 0);
+            cum_s[s] = run;  // inclusive: frames [cum[s-1], cum[s]) belong to column s
+        }
+    }
+    __syncthreads();
+    const int t_y = t_ys ? min(max(t_ys[b], 0), T) : T;
+    for (int y = tid; y < T; y += kScatterThreads) {
+        int lo = 0, hi = t_x;  // first column in [0, t_x) with cum > y, t_x if none
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum_s[mid] > y)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        idx[(size_t)b * T + y] = (y < t_y && lo < t_x) ? lo : -1;
+    }
+}
+
+int idx_from_durations_launch(const float *dur_f, const int32_t *t_xs, const int32_t *t_ys, int32_t *idx, int B, int T,
+                              int S, cudaStream_t stream)
+{
+    mas_idx_from_durations_kernel<<<(unsigned)B, kScatterThreads, 0, stream>>>(dur_f, t_xs, t_ys, idx, T, S);
+    note_launch();
+    MAS_CUDA_TRY(cudaGetLastError());
+    return MAS_OK;
+}
+
 int expand_prior_launch(const float *m_p, const float *logs_p, const int32_t *idx, float *m_out, float *logs_out, int B,
                         int D, int T, int S, cudaStream_t stream)
 {

@@ -91,3 +91,34 @@ def logw(durations: torch.Tensor, x_lengths: torch.Tensor) -> torch.Tensor:
         rc = _lib.lib().mas_logw_f32(_lib.ptr(dur), _lib.ptr(t_xs), _lib.ptr(out), B, S, _lib.stream_ptr(device))
     _lib.check(rc, "mas_logw_f32")
     return out.unsqueeze(1)
+
+
+def idx_from_durations(duration: torch.Tensor, x_lengths: torch.Tensor, T: int, y_lengths=None) -> torch.Tensor:
+    """Inference side: ceil()ed durations [B,S] or [B,1,S] -> compact alignment idx [B,T] int32 (-1 where no text
+    column covers the frame), the compact form of commons.generate_path (commons.py:130-145)."""
+    _lib.require_cuda(duration, "duration")
+    dur = duration.reshape(duration.shape[0], duration.shape[-1]).float().contiguous()
+    B, S = dur.shape
+    device = dur.device
+    t_xs = x_lengths.to(device=device, dtype=torch.int32).contiguous()
+    t_ys = y_lengths.to(device=device, dtype=torch.int32).contiguous() if y_lengths is not None else None
+    with torch.cuda.device(device):
+        idx = torch.empty((B, T), dtype=torch.int32, device=device)
+        rc = _lib.lib().mas_idx_from_durations_f32(_lib.ptr(dur), _lib.ptr(t_xs), _lib.ptr(t_ys), _lib.ptr(idx), B, T, S,
+                                                   _lib.stream_ptr(device))
+    _lib.check(rc, "mas_idx_from_durations_f32")
+    return idx
+
+
+def generate_path(duration: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Drop-in for commons.generate_path(duration [b,1,t_x], mask [b,1,t_y,t_x]) -> path [b,1,t_y,t_x] in mask.dtype.
+    The lengths are read off the mask's first row / column as `maximum_path` does (the mask is an outer product of
+    two length masks, models.py:1309)."""
+    from .monotonic_align import lengths_from_mask
+    from .sharded import expand_path
+
+    _lib.require_cuda(mask, "mask")
+    b, _, t_y, t_x = mask.shape
+    t_ys, t_xs = lengths_from_mask(mask.reshape(b, t_y, t_x))
+    idx = idx_from_durations(duration, t_xs, t_y, t_ys)
+    return expand_path(idx, t_x, mask.dtype).unsqueeze(1)
