@@ -65,11 +65,10 @@ __global__ void __launch_bounds__(kGatherThreads) mas_gather_prior_kernel(const 
 // kScatterChunk frames with coalesced 16-byte loads; a thread then owns a text column (up to 4 for S = 1024)
 // and adds up the part of its segment that lies in the chunk.
 constexpr int kScatterThreads = 256;
-constexpr int kScatterD = 2;
-constexpr int kScatterChunk = 2048;
-constexpr int kScatterCols = (MAS_MAX_TEXT + kScatterThreads - 1) / kScatterThreads;  // 4
+constexpr int kScatterD = 4;
+constexpr int kScatterChunk = 1024;   // frames per tile row = one 16-byte load per thread
 
-template <bool kTwo>
+template <bool kTwo, int kScatterCols>   // kScatterCols = ceil(S / 256) text columns per thread
 __global__ void __launch_bounds__(kScatterThreads) mas_scatter_prior_kernel(const float *__restrict__ g_m,
                                                                             const float *__restrict__ g_logs,
                                                                             const int32_t *__restrict__ dur,
@@ -266,10 +265,19 @@ int expand_prior_backward_launch(const float *g_m, const float *g_logs, const in
                                  int B, int D, int T, int S, cudaStream_t stream)
 {
     const dim3 grid((unsigned)((D + kScatterD - 1) / kScatterD), (unsigned)B);
-    if (g_logs)
-        mas_scatter_prior_kernel<true><<<grid, kScatterThreads, 0, stream>>>(g_m, g_logs, dur, g_m_p, g_logs_p, D, T, S);
-    else
-        mas_scatter_prior_kernel<false><<<grid, kScatterThreads, 0, stream>>>(g_m, g_logs, dur, g_m_p, g_logs_p, D, T, S);
+#define MAS_SCATTER(TWO, COLS) \
+    mas_scatter_prior_kernel<TWO, COLS><<<grid, kScatterThreads, 0, stream>>>(g_m, g_logs, dur, g_m_p, g_logs_p, D, T, S)
+    const int cols = (S + kScatterThreads - 1) / kScatterThreads;
+    if (g_logs) {
+        if (cols <= 1) MAS_SCATTER(true, 1);
+        else if (cols == 2) MAS_SCATTER(true, 2);
+        else MAS_SCATTER(true, 4);
+    } else {
+        if (cols <= 1) MAS_SCATTER(false, 1);
+        else if (cols == 2) MAS_SCATTER(false, 2);
+        else MAS_SCATTER(false, 4);
+    }
+#undef MAS_SCATTER
     note_launch();
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;
