@@ -24,7 +24,9 @@ txd = t_x.to(dev).int()
 
 
 def timed(fn, reps=20):
-    for _ in range(3): fn()
+    for _ in range(3):
+        rc = fn()
+        assert not isinstance(rc, int) or rc == 0, f"C ABI call failed with status {rc}"
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
