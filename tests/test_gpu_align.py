@@ -184,3 +184,15 @@ def test_noise_applied_inside_the_dp(cuda_device, B, S, T, ragged, scale):
     assert _rel_err(nc.cpu(), nc_ref) < REL_TOL
     assert (attn_a.cpu() == attn_ref).float().mean().item() >= MIN_AGREE
     assert torch.equal(w_a.sum((1, 2)).cpu(), w_ref.sum((1, 2)))
+
+
+def test_zero_scale_shortcut_is_the_noise_branch_on_finite_costs(cuda_device):
+    """mas_noise_scale == 0 (where cli.py:268-271 ends up): the noise branch and the fused no-noise kernel agree
+    bit for bit on finite costs, which is what `zero_scale_is_no_noise=True` relies on."""
+    B, S, T = 5, 120, 500
+    t_x, t_y = synthetic.ragged_lengths(B, S, T, 4)
+    args = [t.to(cuda_device) for t in synthetic.prior_inputs(B, S, T, t_x, t_y, seed=13)]
+    noise = torch.randn((B, T, S), device=cuda_device)
+    a0, w0, nc0 = tts.align(*args, 0, noise, return_neg_cent=True)
+    a1, w1, nc1 = tts.align(*args, 0, noise, return_neg_cent=True, zero_scale_is_no_noise=True)
+    assert torch.equal(a0, a1) and torch.equal(w0, w1) and torch.equal(nc0, nc1)

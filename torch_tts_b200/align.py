@@ -40,16 +40,24 @@ def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torc
 
 
 def align(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=None, *,
-          x_lengths=None, y_lengths=None, return_compact: bool = False, return_neg_cent: bool = False):
+          x_lengths=None, y_lengths=None, return_compact: bool = False, return_neg_cent: bool = False,
+          zero_scale_is_no_noise: bool = False):
     """Replacement for models.py:1224-1256.
 
     z_p [B,D,T], m_p/logs_p [B,D,S], x_mask [B,1,S], y_mask [B,1,T].
     mas_noise_scale: None, or the scalar of cli.py:268-271 (0 still takes the
     noise branch, as in the reference).  noise: optional [B,T,S] draw standing
     in for torch.randn_like(neg_cent) (models.py:1244); drawn here when absent.
+    zero_scale_is_no_noise: the schedule of cli.py:268-271 reaches 0 after 5000 steps and stays there;
+    `neg_cent + (std * noise) * 0` is `neg_cent` bit for bit whenever every cost is finite, so with this
+    switch a scale of exactly 0 takes the single fused kernel (no draw, no second pass over the plane).
+    Off by default because the two differ when neg_cent holds a NaN/Inf: the reference's std is then NaN
+    and every cost of the batch with it.
     Returns (attn [B,1,T,S] in z_p.dtype, w [B,1,S]) and, on request, the
     compact (idx, durations, status) and the aligned neg_cent.
     """
+    if zero_scale_is_no_noise and mas_noise_scale is not None and float(mas_noise_scale) == 0.0:
+        mas_noise_scale, noise = None, None
     for n, t in (("z_p", z_p), ("m_p", m_p), ("logs_p", logs_p)):
         _lib.require_cuda(t, n)
     B, D, T = z_p.shape
