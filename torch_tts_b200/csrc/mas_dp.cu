@@ -99,6 +99,14 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, 
                 if (stages_hint > 0) break;
             }
     }
+    if (ok && stages_hint <= 0 && !pl.p.hop_in_smem) {
+        // The search ended on the fully spilled layout.  If the same ring also fits next to on-chip hops, take
+        // that: the backtrack's T/32 dependent hop reads cost ~0.6 us each from L2 and ~30 ns from shared memory
+        // (noise-scaled MAS at S = 256: three 66 KB stages leave room for the 9 KB of hop bytes, not for the
+        // 32 KB of decision words).
+        DpPlan alt = pl;
+        if (dp_plan_try(alt, T, S, W, C, pl.p.R, pl.p.stages, false, true, budget, with_noise, false)) pl = alt;
+    }
     if (!ok) {
         // last resort: no prefetch distance at all
         ok = dp_plan_try(pl, T, S, W, C, R0, W, false, false, budget, with_noise, false);
