@@ -1,14 +1,16 @@
 // mas_fused.cu -- neg_cent contraction and MAS in ONE kernel (no-noise alignment path,
 // reference vits2/models.py:1224-1256 with mas_noise_scale None).
 //
-// One CTA per SM, roles by block index: the first n_gemm CTAs run the tcgen05 contraction
-// (mas_cost_tc.cuh) over the tile list -- utterance groups of n_dp, mel-tile-major inside a
-// group -- and publish every finished 128-row cost tile with a release store to a flag; the
-// last n_dp CTAs run the forward DP + backtrack (mas_dp.cuh), one utterance at a time, and
-// acquire the flag of a tile before the TMA engine streams its rows out of L2.  The cost
-// plane round-trips through L2 only; the DP trails the contraction by a few tiles instead of
-// waiting for the whole batch.  Producers never wait on consumers, and the launch is
-// cooperative so all CTAs are co-resident.
+// One CTA per SM.  Every CTA starts in the tcgen05 contraction role (mas_cost_tc.cuh) over the unit list --
+// utterance groups of n_dp, mel-tile-major inside a group -- and publishes every finished 128-row cost tile with
+// a release store to a flag.  After seq_k rounds the first n_dp CTAs leave the contraction and run the forward
+// DP + backtrack (mas_dp.cuh), one utterance at a time, acquiring the flag of a tile before the TMA engine
+// streams its rows out of L2; the other CTAs finish the units and then drain the zero-fill queue of the path
+// planes.  The cost plane round-trips through L2 only; the DP trails the contraction by a few tiles instead of
+// waiting for the whole batch.  Producers never wait on consumers; the launch is cooperative so that all CTAs
+// are co-resident, and a programmatic dependent of the prior-images kernel (fused_launch).
+#include <atomic>
+
 #include "mas_cost_tc.cuh"
 #include "mas_dp.cuh"
 
@@ -175,7 +177,7 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     // prior-images kernel ahead of it in the stream is still running, and overlaps its prologue (barriers, TMEM,
     // tensor maps) with that kernel; cost_tc_role waits for it before the first dependent read.  Tried once
     // outside stream capture; a driver that refuses the combination gets plain launches from then on.
-    static int pdl_state = -1;  // -1 untested, 0 refused, 1 works
+    static std::atomic<int> pdl_state{-1};  // -1 untested, 0 refused, 1 works (calls may come from several threads)
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cap);
     bool use_pdl = env_int("MAS_FUSED_PDL", 1) && (pdl_state == 1 || (pdl_state < 0 && cap == cudaStreamCaptureStatusNone));
