@@ -12,11 +12,13 @@ namespace mas {
 //   bias_part[b][kb][s] = sum over the 16 channels of the block of
 //     (-0.5 log 2pi - logs_p) + (-0.5 m^2 r);  the contraction's epilogue adds the n_kb
 //     partials in a fixed order (deterministic, no atomics).
-// One CTA per (kb, b), one thread per text column: every global load is coalesced along s
+// One CTA per (kb, b, half of the column block), one thread per text column: every global load is coalesced along s
 // and all 32 loads of a thread are in flight before the first use.  The grid also zeroes the
 // tile flags of the fused kernel.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNMax) mas_prior_images_kernel(const float *__restrict__ m_p,
+constexpr int kPriorThreads = 128;              // two CTAs per image: 1536 small CTAs at config 2 fill the GPU's
+constexpr int kPriorParts = kNMax / kPriorThreads;  // second wave where 768 CTAs of 256 threads left it 70 % idle
+__global__ void __launch_bounds__(kPriorThreads) mas_prior_images_kernel(const float *__restrict__ m_p,
                                                                 const float *__restrict__ logs_p,
                                                                 unsigned char *__restrict__ images,
                                                                 float *__restrict__ bias_part, int D, int S, int n_kb,
@@ -25,12 +27,13 @@ __global__ void __launch_bounds__(kNMax) mas_prior_images_kernel(const float *__
     // let a programmatic dependent (the fused kernel) start its prologue while this grid runs; it waits for
     // this grid's completion before it reads anything written here
     asm volatile("griddepcontrol.launch_dependents;");
-    const int kb = blockIdx.x, b = blockIdx.y, nb = blockIdx.z;   // K block, utterance, column block
-    const int s_img = threadIdx.x;                                // row of the image
+    const int kb = blockIdx.x, b = blockIdx.y;                    // K block, utterance
+    const int nb = blockIdx.z / kPriorParts, n_blocks = gridDim.z / kPriorParts;   // column block (of kNMax columns)
+    const int s_img = (blockIdx.z % kPriorParts) * kPriorThreads + threadIdx.x;    // row of the image
     const int s = nb * kNMax + s_img;                             // text column
     if (flags_to_clear) {
         const int n_cta = gridDim.x * gridDim.y * gridDim.z, cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        for (int i = cta * kNMax + s_img; i < n_flags; i += n_cta * kNMax) flags_to_clear[i] = 0u;
+        for (int i = cta * kPriorThreads + threadIdx.x; i < n_flags; i += n_cta * kPriorThreads) flags_to_clear[i] = 0u;
     }
     const bool live = s < S;
     const size_t base = (size_t)b * D * S + (live ? s : 0);
@@ -55,8 +58,8 @@ __global__ void __launch_bounds__(kNMax) mas_prior_images_kernel(const float *__
         acc4 += -0.5f * (m[j] * m[j]) * rr;                // :1236-1238 (0 when !ok)
         m[j] = m[j] * rr;                                  // m r, :1234
     }
-    unsigned char *img_hi = images + (((size_t)(b * gridDim.z + nb) * n_kb + kb) * 2 + 0) * kBPart;
-    unsigned char *img_lo = images + (((size_t)(b * gridDim.z + nb) * n_kb + kb) * 2 + 1) * kBPart;
+    unsigned char *img_hi = images + (((size_t)(b * n_blocks + nb) * n_kb + kb) * 2 + 0) * kBPart;
+    unsigned char *img_lo = images + (((size_t)(b * n_blocks + nb) * n_kb + kb) * 2 + 1) * kBPart;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {      // 0: r, 1: m r
 #pragma unroll
@@ -129,7 +132,7 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
     if (stats_out) MAS_CUDA_TRY(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double), stream));
     const char *dbg = getenv("MAS_TC_DEBUG");  // bit 16: reuse the images already in the workspace (timing experiments)
     if (!(dbg && *dbg && (atoi(dbg) & 16))) {
-        mas_prior_images_kernel<<<dim3(n_kb, B, n_blocks), kNMax, 0, stream>>>(m_p, logs_p, images, bias, D, S, n_kb,
+        mas_prior_images_kernel<<<dim3(n_kb, B, n_blocks * kPriorParts), kPriorThreads, 0, stream>>>(m_p, logs_p, images, bias, D, S, n_kb,
                                                                      flags_to_clear, n_flags);
         note_launch();
         MAS_CUDA_TRY(cudaGetLastError());
