@@ -28,7 +28,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     p.off_bar = (uint32_t)off;
     off += 128;
     p.off_bits = (uint32_t)off;
-    if (bits_smem) off += align_up((size_t)n_blk * S_pad * 4, 16);
+    if (bits_smem) off += align_up((size_t)n_blk * (S_pad + kBitsPad) * 4, 16);
     p.off_hop = (uint32_t)off;
     if (hop_smem) off += align_up((size_t)hop_rows * S_pad, 16);
     p.stage_bytes = (uint32_t)align_up((size_t)R * S * 4 + 16 + 64, 128);  // tile + misalignment + zeroed pad
@@ -53,7 +53,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     off += 16;
     p.bits_in_smem = bits_smem;
     p.hop_in_smem = hop_smem;
-    p.bits_words_per_cta = (unsigned long long)n_blk * S_pad;
+    p.bits_words_per_cta = (unsigned long long)n_blk * (S_pad + kBitsPad);
     p.hop_bytes_per_cta = (unsigned long long)align_up((size_t)hop_rows * S_pad, 16);
     pl.smem_bytes = off;
     pl.C = C;

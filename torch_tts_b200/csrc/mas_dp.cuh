@@ -46,6 +46,7 @@ constexpr uint32_t kZeroFillBuf = 32768;  // zero page of the zero-fill role (co
 constexpr int kZeroParts = 8;             // slices per path plane handed out by the zero-fill role
 
 // mel rows per chunk (= per TMA tile) for S text columns: a stage stays <= 32 KB
+constexpr int kBitsPad = 4;   // words between decision-word rows beyond S_pad (keeps 16-byte alignment)
 __host__ __device__ constexpr int dp_chunk_rows(int S) { return S <= 256 ? 32 : (S <= 512 ? 16 : 8); }
 
 struct DpParams {
@@ -411,6 +412,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     const int T = p.T, S = p.S;
     const int t_y = p.t_ys[b], t_x = p.t_xs[b];
     constexpr int S_pad = W * 32 * C;
+    constexpr int S_bits = S_pad + kBitsPad;
     static_assert(!kVK || R == kCheck, "the warp split replays whole decision words: one chunk = one word");
     constexpr int kThreads = dp_threads(W, kVK);
     constexpr int kDpWarps = W;                       // warps that consume cost tiles
@@ -438,7 +440,8 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     }
 
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
-    // decision bits: word [(y >> 5) * S_pad + x], bit (y & 31)
+    // decision bits: word [(y >> 5) * S_bits + x], bit (y & 31); S_bits = S_pad + kBitsPad so that the backtrack's
+    // walks (one thread per 32-row block, all near the same column) do not all hit one shared-memory bank
     uint32_t *bits = p.bits_in_smem ? reinterpret_cast<uint32_t *>(smem + p.off_bits)
                                     : p.bits_ws + (size_t)slot * p.bits_words_per_cta;
     unsigned char *hop = p.hop_in_smem ? (smem + p.off_hop) : p.hop_ws + (size_t)slot * p.hop_bytes_per_cta;
@@ -591,7 +594,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
                     const int slot0 = (c & 1) * R;
-                    const uint32_t *wrow = bits + (size_t)(row0 >> 5) * S_pad + x0;
+                    const uint32_t *wrow = bits + (size_t)(row0 >> 5) * S_bits + x0;
                     uint32_t wd[C];
 #pragma unroll
                     for (int k = 0; k < C; ++k) wd[k] = wrow[k];
@@ -689,7 +692,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         wl[k] = 0u;
                     }
                     if (word_done) {
-                        uint32_t *wrow = bits + (size_t)((end_row - 1) >> 5) * S_pad + x0;
+                        uint32_t *wrow = bits + (size_t)((end_row - 1) >> 5) * S_bits + x0;
                         if (C % 4 == 0) {
 #pragma unroll
                             for (int k = 0; k < C; k += 4)
@@ -773,9 +776,11 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             y_top = y_last;
             cur = t_x - 1;
         }
+        // (all rows of a walk lie in one 32-row block: one decision-word row, and the bit index is y - 32 j)
+        const uint32_t *wrow = bits + (size_t)(y_top >> 5) * S_bits;
         for (int y = y_top; y >= y_lo; --y) {
             idx_s[y] = (uint16_t)cur;
-            const uint32_t wd = bits[(size_t)(y >> 5) * S_pad + cur];
+            const uint32_t wd = wrow[cur];
             cur -= (cur != 0) ? (int)((wd >> (y & 31)) & 1u) : 0;  // core.pyx:32 "index != 0 and ..."
         }
     }
