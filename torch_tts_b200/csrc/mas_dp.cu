@@ -44,7 +44,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     p.off_zero = (uint32_t)off;
     off += kZeroBytes;
     p.off_idx = (uint32_t)off;
-    off += align_up((size_t)T * 2 + 2, 16);
+    off += align_up(T <= 2048 ? (size_t)32 * ((T >> 5) + 2) * 2 : (size_t)T * 2 + 2, 16);   // idx_s (dp_role: ix())
     p.off_end = (uint32_t)off;
     off += (size_t)S_pad * 4;
     p.off_entry = (uint32_t)off;

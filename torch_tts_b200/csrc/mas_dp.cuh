@@ -448,6 +448,11 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);  // [kDpWarps + 1][2R]
     int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
     uint16_t *idx_s = reinterpret_cast<uint16_t *>(smem + p.off_idx);
+    // the column of mel row y sits at idx_s[ix(y)]: block-minor, so that the 32-row walks of the backtrack (one
+    // thread per block, all at the same row offset) store to consecutive addresses instead of two banks
+    // (short utterances only: at T = 4000 the linear layout measured 8 % faster for the whole kernel)
+    const int idx_pitch = (T <= 2048) ? (T >> 5) + 2 : 0;
+    auto ix = [idx_pitch](int y) { return idx_pitch ? (y & 31) * idx_pitch + (y >> 5) : y; };
     int *end_s = reinterpret_cast<int *>(smem + p.off_end);
     uint16_t *entry_s = reinterpret_cast<uint16_t *>(smem + p.off_entry);
     unsigned char *zero_s = smem + p.off_zero;
@@ -761,7 +766,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             c -= hop[(size_t)j * S_pad + c];  // column at row c_{j-1}
             entry_s[j - 1] = (uint16_t)c;
         }
-        idx_s[0] = 0;
+        idx_s[ix(0)] = 0;
         if (p.trace) p.trace[12288 + (size_t)b * 32 + 26] = globaltimer_ns();
     }
     bar_sync(bar, kThreads);
@@ -779,7 +784,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         // (all rows of a walk lie in one 32-row block: one decision-word row, and the bit index is y - 32 j)
         const uint32_t *wrow = bits + (size_t)(y_top >> 5) * S_bits;
         for (int y = y_top; y >= y_lo; --y) {
-            idx_s[y] = (uint16_t)cur;
+            idx_s[ix(y)] = (uint16_t)cur;
             const uint32_t wd = wrow[cur];
             cur -= (cur != 0) ? (int)((wd >> (y & 31)) & 1u) : 0;  // core.pyx:32 "index != 0 and ..."
         }
@@ -797,12 +802,12 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
 
     // =================== outputs ===================
     for (int y = tid; y < t_y; y += kThreads) {
-        const int c = idx_s[y];
+        const int c = idx_s[ix(y)];
         store_one(path_b, (size_t)y * S + c, p.path_dtype);
-        if (y == y_last || idx_s[y + 1] != c) end_s[c] = y;
+        if (y == y_last || idx_s[ix(y + 1)] != c) end_s[c] = y;
     }
     if (p.idx) {
-        for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = (y < t_y) ? (int)idx_s[y] : -1;
+        for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = (y < t_y) ? (int)idx_s[ix(y)] : -1;
     }
     if (p.status && tid == 0) p.status[b] = MAS_UTT_OK;
     if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 30] = globaltimer_ns();
