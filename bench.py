@@ -165,7 +165,7 @@ def run_reference(args):
     value = B * args.steps / dt
     threads = torch.get_num_threads()
     sample = f"{args.steps} passes over one full B={B} batch (torch CPU neg_cent on {threads} threads + serial Cython MAS)"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -368,7 +368,7 @@ def run_b200(args):
         step_s = ms * 1e-3 / args.steps
         fused = {"bound": "hbm", "achieved": FUSED_BYTES * B / step_s / 1e9, "peak": hbm, "unit": "GB/s"}
         fused["frac"] = fused["achieved"] / hbm
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -386,8 +386,27 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(obj) -> None:
+    """The one JSON line, on the process's ORIGINAL stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    global _RESULT_FD
     args = parse()
+    # stdout carries exactly one JSON line: native libraries that print to fd 1 (NCCL's version banner under
+    # torchrun) are sent to stderr for the rest of the run, and the result goes out on a copy of the real stdout
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
