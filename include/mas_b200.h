@@ -88,8 +88,10 @@ int mas_lengths_from_mask_f32(const float *mask, int32_t *t_ys, int32_t *t_xs,
  * of the Python wrapper (__init__.py:14,19).
  *   - neg_cent is read-only (the reference's in-place DP works on a private copy,
  *     __init__.py:13).
- *   - path_out is fully written (zeros included); it need not be pre-zeroed.
- *   - dur_out, idx_out, status_out may be NULL.
+ *   - path_out is fully written (zeros included); it need not be pre-zeroed.  It may be NULL (ABI >= 2): the
+ *     alignment then comes back in compact form only (idx_out / dur_out), the dense plane -- half of the
+ *     algorithmic bytes -- is neither zero-filled nor scattered.  mas_expand_path() rebuilds it on demand.
+ *   - dur_out, idx_out, status_out may be NULL (not all three of path_out, dur_out, idx_out).
  *   - workspace: mas_maximum_path_workspace_bytes(B,T,S) bytes, 256-byte aligned.
  */
 size_t mas_maximum_path_workspace_bytes(int B, int T, int S);
@@ -121,8 +123,11 @@ int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p,
  *     and adds (std * noise) * noise_scale (:1242-1247).
  *   - neg_cent_out: optional [B,T,S] float32 copy of the cost actually aligned (with noise: the noised
  *     cost; without this request the noised plane is never written -- the DP adds the noise on the fly).
- *   - no noise, S <= 256, S % 4 == 0, T % 4 == 0: ONE kernel runs contraction and DP concurrently
- *     (cooperative launch; needs the whole GPU like any persistent kernel).
+ *   - path_out may be NULL (compact outputs only), as in mas_maximum_path_f32.
+ *   - S <= 256 and no neg_cent_out request: ONE kernel (after the prior preparation) runs contraction and DP --
+ *     concurrently without noise; with noise around a grid barrier, B <= 74 (the statistics of models.py:1243
+ *     must exist before the first DP row).  Cooperative launch: needs the whole GPU like any persistent kernel;
+ *     where the context cannot hold the grid (MPS / MIG limits) the same work runs as separate launches.
  */
 size_t mas_fused_align_workspace_bytes(int B, int D, int T, int S, int with_noise);
 int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
@@ -178,7 +183,11 @@ int mas_logw_f32(const int32_t *dur, const int32_t *t_xs, float *logw_out,
 int mas_idx_from_durations_f32(const float *durations, const int32_t *t_xs, const int32_t *t_ys,
                                int32_t *idx_out, int B, int T, int S, void *stream);
 
-/* diagnostics: with MAS_TRACE=1 in the environment the fused kernel records device timestamps
+/* Tuning knobs (MAS_NO_FUSED, MAS_DP_VK, MAS_DP_WARPS, ... see csrc/mas_common.cuh) are read from the environment
+ * once, on first use; this re-reads them (tests and benchmarks that switch variants inside one process). */
+void mas_reload_config(void);
+
+/* diagnostics (trace build of the library only, -DMAS_TRACE): with MAS_TRACE=1 in the environment the fused kernel records device timestamps
  * (ns, %globaltimer) of tile publications and DP milestones; this copies the first n_words of the
  * trace to the host (synchronises the device).  MAS_ERR_NULL_POINTER when tracing is off. */
 int mas_debug_read_trace(unsigned long long *host_out, int n_words);

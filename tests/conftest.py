@@ -13,6 +13,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 with -m gpu)")
 
 
+@pytest.fixture
+def mas_env(monkeypatch):
+    """Set MAS_* tuning knobs for one test.  The library reads them once, so it is told to re-read them now
+    and again after the environment has been restored."""
+    from torch_tts_b200 import _lib
+
+    def set_env(**kv):
+        for k, v in kv.items():
+            monkeypatch.setenv(k, str(v))
+        _lib.reload_config()
+
+    yield set_env
+    monkeypatch.undo()
+    _lib.reload_config()
+
+
 @pytest.fixture(scope="session")
 def cuda_device():
     import torch

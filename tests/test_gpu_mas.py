@@ -164,10 +164,10 @@ def test_full_size_invariants(cuda_device):
 
 @pytest.mark.parametrize("vk", ["1", "0"])
 @pytest.mark.parametrize("B,S,T,ties", [(4, 256, 1024, False), (3, 100, 333, True), (5, 64, 64, False), (2, 200, 40 * 32 + 1, True)])
-def test_value_origin_warp_split(cuda_device, monkeypatch, B, S, T, ties, vk):
+def test_value_origin_warp_split(cuda_device, mas_env, B, S, T, ties, vk):
     """The forward DP on value warps + origin warps (MAS_DP_VK, the default where the shape allows it) and on
     single-role warps (MAS_DP_VK=0, what noise-scaled MAS and long texts use) are both bit-exact."""
-    monkeypatch.setenv("MAS_DP_VK", vk)
+    mas_env(MAS_DP_VK=vk)
     nc = synthetic.neg_cent_like(B, S, T, seed=S + T, ties=ties)
     t_x, t_y = synthetic.ragged_lengths(B, S, T, seed=B)
     t_y = torch.maximum(t_y, t_x)

@@ -66,3 +66,50 @@ def test_gather_compact_world2_gloo(tmp_path, batch):
         assert np.array_equal(g_idx.numpy(), want_idx)
         assert np.array_equal(g_dur.numpy(), full.sum(1))
         assert torch.equal(g_dur.sum(1), t_y)
+
+
+def _worker_ragged_shapes(rank, world, port, out_dir):
+    """every rank pads its own batch to its own T and S, and holds a different number of utterances"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import mas_oracle
+
+        n, S, T = [(3, 19, 80), (5, 23, 64)][rank]
+        t_x, t_y = synthetic.ragged_lengths(n, S, T, seed=30 + rank)
+        nc = synthetic.neg_cent_like(n, S, T, seed=30 + rank)
+        path = mas_oracle.maximum_path_c(nc.numpy(), t_y.numpy(), t_x.numpy())
+        idx = torch.from_numpy(np.where(path.sum(2) > 0, path.argmax(2), -1).astype(np.int32))
+        dur = torch.from_numpy(path.sum(1).astype(np.int32))
+        g_idx, g_dur = sharded.gather_compact(idx, dur)
+        torch.save((g_idx, g_dur), os.path.join(out_dir, f"rank{rank}.pt"))
+        with pytest.raises(RuntimeError):
+            sharded.gather_compact(idx, dur, batch=99)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_compact_ranks_with_different_shapes(tmp_path):
+    """DDP ranks pad to their own T / S (data_utils.py:168-177); the gather must not assume one shape."""
+    from oracle import mas_oracle
+
+    world = 2
+    mp.spawn(_worker_ragged_shapes, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want_idx, want_dur = [], []
+    Tg, Sg = 80, 23
+    for rank, (n, S, T) in enumerate([(3, 19, 80), (5, 23, 64)]):
+        t_x, t_y = synthetic.ragged_lengths(n, S, T, seed=30 + rank)
+        nc = synthetic.neg_cent_like(n, S, T, seed=30 + rank)
+        path = mas_oracle.maximum_path_c(nc.numpy(), t_y.numpy(), t_x.numpy())
+        idx = np.full((n, Tg), -1, np.int64)
+        idx[:, :T] = np.where(path.sum(2) > 0, path.argmax(2), -1)
+        dur = np.zeros((n, Sg), np.int64)
+        dur[:, :S] = path.sum(1)
+        want_idx.append(idx)
+        want_dur.append(dur)
+    want_idx, want_dur = np.concatenate(want_idx), np.concatenate(want_dur)
+    for r in range(world):
+        g_idx, g_dur = torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"))
+        assert g_idx.shape == (8, Tg) and g_dur.shape == (8, Sg)
+        assert np.array_equal(g_idx.numpy(), want_idx) and np.array_equal(g_dur.numpy(), want_dur)

@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "mas_fused_align_workspace_bytes", "mas_fused_align_f32",
     "mas_expand_path", "mas_expand_prior_f32", "mas_expand_prior_backward_f32", "mas_logw_f32",
     "mas_idx_from_durations_f32",
-    "mas_take_launch_count", "mas_debug_read_trace",
+    "mas_take_launch_count", "mas_debug_read_trace", "mas_reload_config",
 )
 
 PATH_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.int32: 3}
@@ -68,6 +68,7 @@ def lib():
                 L.mas_fused_align_f32.restype = i32
                 L.mas_fused_align_f32.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp, i32, vp, vp, vp, vp, vp, sz,
                                                   i32, i32, i32, i32, vp]
+                L.mas_reload_config.restype = None
                 L.mas_debug_read_trace.restype = i32
                 L.mas_debug_read_trace.argtypes = [vp, i32]
                 L.mas_expand_path.restype = i32
@@ -82,6 +83,11 @@ def lib():
                 L.mas_idx_from_durations_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
                 _lib = L
     return _lib
+
+
+def reload_config():
+    """Re-read the MAS_* tuning knobs from the environment (the library reads them once, on first use)."""
+    lib().mas_reload_config()
 
 
 def check(rc: int, what: str):

@@ -8,6 +8,38 @@ import torch
 from . import _lib
 
 
+class CompactAlignment:
+    """The alignment in compact form: `idx` [B,T] int32 (text column of every mel frame, -1 past
+    the mel length), `durations` [B,S] int32 (= attn.sum(2), models.py:1256) and the per-utterance `status`.
+    The dense one-hot `attn` [B,1,T,S] that the reference builds (models.py:1250-1254) -- half of the alignment's
+    memory traffic, and only ever consumed again by two matmuls that `expand_prior` replaces and by the TensorBoard
+    image hook (train_ms.py:517-519, cli.py:53-59) -- is built on first use of `.attn()` and cached."""
+
+    def __init__(self, idx, durations, status, S: int, dtype):
+        self.idx, self.durations, self.status = idx, durations, status
+        self.S, self.dtype = S, dtype
+        self._attn = None
+
+    def attn(self):
+        if self._attn is None:
+            from .sharded import expand_path
+
+            self._attn = expand_path(self.idx, self.S, self.dtype).unsqueeze(1)
+        return self._attn
+
+    @property
+    def w(self):
+        return self.durations.to(self.dtype).unsqueeze(1)
+
+    def check(self):
+        """Raise if any utterance violated 1 <= t_x <= t_y <= T (one small device -> host copy)."""
+        bad = torch.nonzero(self.status).flatten().tolist()
+        if bad:
+            raise _lib.MasError(f"utterances {bad[:8]}{'...' if len(bad) > 8 else ''} have text/mel lengths the "
+                                "reference leaves undefined (need 1 <= t_x <= t_y <= T, t_x <= S): no alignment")
+        return self
+
+
 def _lengths(x_mask, y_mask):
     # what mask.sum(1)[:,0] / mask.sum(2)[:,0] give for attn_mask = x_mask[:,:,None] * y_mask[...,None]
     # (models.py:1249, __init__.py:16-17)
@@ -41,7 +73,7 @@ def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torc
 
 def align(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=None, *,
           x_lengths=None, y_lengths=None, return_compact: bool = False, return_neg_cent: bool = False,
-          zero_scale_is_no_noise: bool = False):
+          zero_scale_is_no_noise: bool = False, dense: bool = True, check_status: bool = False):
     """Replacement for models.py:1224-1256.
 
     z_p [B,D,T], m_p/logs_p [B,D,S], x_mask [B,1,S], y_mask [B,1,T].
@@ -53,6 +85,14 @@ def align(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=None, *,
     switch a scale of exactly 0 takes the single fused kernel (no draw, no second pass over the plane).
     Off by default because the two differ when neg_cent holds a NaN/Inf: the reference's std is then NaN
     and every cost of the batch with it.
+    dense=False: the dense attn is never written (no zero fill, no scatter: the call moves about half the
+    bytes); the first result is then a `CompactAlignment` (idx / durations / status, `.attn()` expands lazily).
+    check_status=True: raise if an utterance has lengths outside 1 <= t_x <= t_y <= T (costs one tiny
+    device -> host copy, i.e. a sync); without it such an utterance silently gets an all-zero path, zero
+    durations and status 1 -- where the reference would read out of bounds.  Callers who keep the default must
+    look at `status` themselves (return_compact=True).
+    Note: the reference's default config (use_noise_scaled_mas, cli.py:268-271) always passes a number, also
+    after the schedule has decayed to 0; pass zero_scale_is_no_noise=True to let scale 0 take the no-noise kernel.
     Returns (attn [B,1,T,S] in z_p.dtype, w [B,1,S]) and, on request, the
     compact (idx, durations, status) and the aligned neg_cent.
     """
@@ -79,7 +119,7 @@ def align(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=None, *,
         kdtype = dtype if dtype in _lib.PATH_DTYPES else torch.float32
         L = _lib.lib()
         with torch.cuda.device(device):
-            path = torch.empty((B, T, S), dtype=kdtype, device=device)
+            path = torch.empty((B, T, S), dtype=kdtype, device=device) if dense else None
             dur = torch.empty((B, S), dtype=torch.int32, device=device)
             idx = torch.empty((B, T), dtype=torch.int32, device=device)
             status = torch.empty((B,), dtype=torch.int32, device=device)
@@ -94,9 +134,15 @@ def align(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=None, *,
                                        _lib.ptr(nc_out), _lib.ptr(ws), ws.numel(), B, D, T, S,
                                        _lib.stream_ptr(device))
         _lib.check(rc, "mas_fused_align_f32")
-        if kdtype != dtype:
-            path = path.to(dtype)
-        attn = path.unsqueeze(1)                       # models.py:1252
+        compact = CompactAlignment(idx, dur, status, S, dtype)
+        if check_status:
+            compact.check()
+        if dense:
+            if kdtype != dtype:
+                path = path.to(dtype)
+            attn = path.unsqueeze(1)                   # models.py:1252
+        else:
+            attn = compact
         w = dur.to(dtype).unsqueeze(1)                 # models.py:1256  attn.sum(2)
     out = (attn, w)
     if return_compact:

@@ -4,7 +4,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "mas_common.cuh"
+#include "mas_fused.cuh"
 
 namespace mas {
 
@@ -13,19 +16,62 @@ static thread_local char g_cuda_err[256] = "";
 
 void note_launch(int n) { g_launches += n; }
 
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+static Config g_config;
+static std::once_flag g_config_once;
+static std::mutex g_config_mutex;
+
+static void read_config()
+{
+    Config c{};
+    c.no_fused = env_int("MAS_NO_FUSED", 0);
+    c.dp_vk = env_int("MAS_DP_VK", 1);
+    c.dp_warps = env_int("MAS_DP_WARPS", 0);
+    c.dp_stages = env_int("MAS_DP_STAGES", 0);
+    c.fused_dp_ctas = env_int("MAS_FUSED_DP_CTAS", 0);
+    c.fused_rounds = env_int("MAS_FUSED_ROUNDS", -1);
+    c.fused_zero_offload = env_int("MAS_FUSED_ZERO_OFFLOAD", 1);
+    c.fused_pdl = env_int("MAS_FUSED_PDL", 1);
+    c.noise_fused = env_int("MAS_NOISE_FUSED", 1);
+    c.stage = env_int("MAS_STAGE", 0);
+    c.tc_pair = 1;
+    if (kTrace) {
+        c.tc_debug = env_int("MAS_TC_DEBUG", 0);
+        c.dp_debug = env_int("MAS_DP_DEBUG", 0);
+        c.tc_no_tma = env_int("MAS_TC_NO_TMA", 0);
+        c.tc_grid = env_int("MAS_TC_GRID", 0);
+        c.tc_pair = env_int("MAS_TC_PAIR", 1);
+        c.trace = env_int("MAS_TRACE", 0);
+    }
+    std::lock_guard<std::mutex> lock(g_config_mutex);
+    g_config = c;
+}
+
+const Config &config()
+{
+    std::call_once(g_config_once, read_config);
+    return g_config;
+}
+
+// trace build + MAS_TRACE=1: one buffer per device, allocated on first use
 unsigned long long *trace_buffer()
 {
-    static unsigned long long *buf = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        const char *e = getenv("MAS_TRACE");
-        if (e && *e && atoi(e)) {
-            if (cudaMalloc(&buf, kTraceWords * sizeof(unsigned long long)) != cudaSuccess) buf = nullptr;
-            if (buf) cudaMemset(buf, 0, kTraceWords * sizeof(unsigned long long));
-        }
+    if (!kTrace || !config().trace) return nullptr;
+    static unsigned long long *bufs[64] = {};
+    static std::mutex m;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(m);
+    if (!bufs[dev]) {
+        if (cudaMalloc(&bufs[dev], kTraceWords * sizeof(unsigned long long)) != cudaSuccess) bufs[dev] = nullptr;
+        if (bufs[dev]) cudaMemset(bufs[dev], 0, kTraceWords * sizeof(unsigned long long));
     }
-    return buf;
+    return bufs[dev];
 }
 
 int note_cuda_error(cudaError_t e, const char *what)
@@ -58,13 +104,6 @@ int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *
                 cudaStream_t stream);
 int add_noise_launch(const float *nc, const float *noise, const double *stats, float scale, float *out, size_t n,
                      cudaStream_t stream);
-// mas_fused.cu
-bool fused_supported(int B, int D, int T, int S);
-size_t fused_flags_bytes(int B, int T);
-int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const int32_t *t_ys, const int32_t *t_xs,
-                 float *neg_cent, bool skip_dead_tiles, void *path_out, int path_dtype, int32_t *dur_out,
-                 int32_t *idx_out, int32_t *status_out, void *cost_ws, size_t cost_ws_bytes, void *dp_ws,
-                 size_t dp_ws_bytes, uint32_t *flags, int B, int D, int T, int S, cudaStream_t stream);
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -86,7 +125,13 @@ using namespace mas;
 
 extern "C" {
 
-int mas_b200_abi_version(void) { return 1; }
+int mas_b200_abi_version(void) { return 2; }   // 2: path_out may be NULL (compact outputs only), mas_reload_config
+
+void mas_reload_config(void)
+{
+    (void)config();
+    read_config();
+}
 
 const char *mas_status_string(int code)
 {
@@ -129,7 +174,8 @@ int mas_maximum_path_f32(const float *neg_cent, const int32_t *t_ys, const int32
                          int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
                          size_t workspace_bytes, int B, int T, int S, void *stream)
 {
-    if (!neg_cent || !t_ys || !t_xs || !path_out) return MAS_ERR_NULL_POINTER;
+    if (!neg_cent || !t_ys || !t_xs) return MAS_ERR_NULL_POINTER;
+    if (!path_out && !dur_out && !idx_out) return MAS_ERR_NULL_POINTER;   // nothing to write
     int rc = check_shape(B, T, S);
     if (rc) return rc;
     rc = check_dtype(path_dtype);
@@ -158,12 +204,12 @@ int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p, fl
                        static_cast<cudaStream_t>(stream));
 }
 
-// fused workspace layout: [cost ws][stats 256 B][neg_cent plane][dp ws][tile flags]
+// fused workspace layout: [cost ws][stats 256 B][private cost plane, rows padded to 16 bytes][dp ws][flags]
 size_t mas_fused_align_workspace_bytes(int B, int D, int T, int S, int with_noise)
 {
     (void)with_noise;
     if (check_shape(B, T, S) != MAS_OK || D < 1) return 0;
-    return align_up(cost_workspace_bytes(B, D, T, S), 256) + 256 + align_up((size_t)B * T * S * 4, 256) +
+    return align_up(cost_workspace_bytes(B, D, T, S), 256) + 256 + fused_plane_bytes(B, T, S) +
            align_up(dp_workspace_bytes(B, T, S), 256) + fused_flags_bytes(B, T);
 }
 
@@ -172,14 +218,15 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
                         int32_t *dur_out, int32_t *idx_out, int32_t *status_out, float *neg_cent_out, void *workspace,
                         size_t workspace_bytes, int B, int D, int T, int S, void *stream)
 {
-    if (!z_p || !m_p || !logs_p || !t_ys || !t_xs || !path_out) return MAS_ERR_NULL_POINTER;
+    if (!z_p || !m_p || !logs_p || !t_ys || !t_xs) return MAS_ERR_NULL_POINTER;
+    if (!path_out && !dur_out && !idx_out) return MAS_ERR_NULL_POINTER;   // nothing to write
     int rc = check_shape(B, T, S);
     if (rc) return rc;
     if (D < 1) return MAS_ERR_BAD_SHAPE;
     rc = check_dtype(path_dtype);
     if (rc) return rc;
     if (!aligned16(z_p) || !aligned16(m_p) || !aligned16(logs_p) || !aligned16(workspace) ||
-        (noise && !aligned16(noise)) || (neg_cent_out && !aligned16(neg_cent_out)))
+        (neg_cent_out && !aligned16(neg_cent_out)))
         return MAS_ERR_ALIGNMENT;
     if (!workspace || workspace_bytes < mas_fused_align_workspace_bytes(B, D, T, S, noise != nullptr))
         return MAS_ERR_WORKSPACE;
@@ -187,20 +234,25 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     const size_t cost_ws = align_up(cost_workspace_bytes(B, D, T, S), 256);
     double *stats = reinterpret_cast<double *>(ws + cost_ws);
-    float *nc = neg_cent_out ? neg_cent_out : reinterpret_cast<float *>(ws + cost_ws + 256);
-    unsigned char *dp_ws = ws + cost_ws + 256 + align_up((size_t)B * T * S * 4, 256);
+    float *plane = reinterpret_cast<float *>(ws + cost_ws + 256);
+    unsigned char *dp_ws = ws + cost_ws + 256 + fused_plane_bytes(B, T, S);
     const size_t dp_ws_bytes = align_up(dp_workspace_bytes(B, T, S), 256);
-    if (!noise && fused_supported(B, D, T, S)) {
-        // one kernel: contraction CTAs publish cost tiles, DP CTAs consume them (mas_fused.cu)
+    // One kernel (plus the prior preparation) when the cost plane can stay private: without noise the DP trails
+    // the contraction tile by tile; with noise the kernel has a grid barrier between them (mas_fused.cu).
+    if (!neg_cent_out && (noise ? fused_noise_supported(B, D, T, S) : fused_supported(B, D, T, S))) {
         uint32_t *flags = reinterpret_cast<uint32_t *>(dp_ws + dp_ws_bytes);
-        return fused_launch(z_p, m_p, logs_p, t_ys, t_xs, nc, neg_cent_out == nullptr, path_out, path_dtype, dur_out,
-                            idx_out, status_out, ws, cost_ws, dp_ws, dp_ws_bytes, flags, B, D, T, S, st);
+        rc = fused_launch(z_p, m_p, logs_p, t_ys, t_xs, noise, noise_scale, stats, plane, path_out, path_dtype, dur_out,
+                          idx_out, status_out, ws, cost_ws, dp_ws, dp_ws_bytes, flags, B, D, T, S, st);
+        if (rc != kFusedFallback) return rc;
+        // the cooperative grid does not fit this context: the same work as separate launches below
     }
     // mel tiles wholly past t_y are skipped only when the plane is private scratch: a caller who asked for
     // neg_cent_out gets every cell the reference would compute
+    float *nc = neg_cent_out ? neg_cent_out : plane;
     rc = cost_launch(z_p, m_p, logs_p, nc, noise ? stats : nullptr, neg_cent_out ? nullptr : t_ys, ws, cost_ws, B, D,
                      T, S, st);
     if (rc) return rc;
+    if (config().stage == 1) return MAS_OK;
     if (noise && (neg_cent_out || !dp_noise_supported(nc, noise, S))) {
         // the caller wants the noised cost plane itself (or the rows are not 16-byte): one more pass
         rc = add_noise_launch(nc, noise, stats, noise_scale, nc, (size_t)B * T * S, st);

@@ -15,12 +15,44 @@ namespace mas {
 constexpr float kNeg = -1e9f;  // core.pyx:7 max_neg_val (exactly representable)
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// ---- diagnostics are a compile-time choice -----------------------------------
+// The product library is built without MAS_TRACE: no timestamp stores, no debug-bit branches in the role
+// loops.  `python -m torch_tts_b200.build --trace` builds libmas_b200_trace.so with -DMAS_TRACE for the
+// timeline tools under tools/ (select it with MAS_LIB_PATH).
+#ifdef MAS_TRACE
+constexpr bool kTrace = true;
+#else
+constexpr bool kTrace = false;
+#endif
+// debug bit `bit` of a role's parameter block (always false in the product build)
+#define MAS_DBG(p, bit) (::mas::kTrace && (((p).debug & (bit)) != 0))
+// the role's trace buffer, or nullptr (always nullptr in the product build)
+#define MAS_TR(p) (::mas::kTrace ? (p).trace : nullptr)
+
 // ---- host-side bookkeeping (defined in mas_api.cu) -------------------------
 void note_launch(int n = 1);
-// MAS_TRACE=1: device buffer of kTraceWords timestamps the fused kernel fills (diagnostics), else nullptr
+// trace build with MAS_TRACE=1 in the environment: device buffer of kTraceWords timestamps (per device), else nullptr
 unsigned long long *trace_buffer();
 constexpr int kTraceWords = 1 << 16;
 int note_cuda_error(cudaError_t e, const char *what);
+
+// Tuning knobs, read from the environment ONCE (first use) and again only on mas_reload_config():
+// no getenv on the launch path.
+struct Config {
+    int no_fused;        // MAS_NO_FUSED=1: contraction and DP as separate launches
+    int dp_vk;           // MAS_DP_VK=0: single-role DP warps instead of the value / origin split
+    int dp_warps;        // MAS_DP_WARPS=4: four value warps with two columns per thread (128 < S <= 256)
+    int dp_stages;       // MAS_DP_STAGES=n: force the cost-tile ring depth
+    int fused_dp_ctas;   // MAS_FUSED_DP_CTAS=n: DP CTAs of the fused kernel (0 = cost model)
+    int fused_rounds;    // MAS_FUSED_ROUNDS=k: contraction rounds before the DP CTAs leave (-1 = cost model)
+    int fused_zero_offload;  // MAS_FUSED_ZERO_OFFLOAD=0: the DP CTAs zero-fill their own path planes
+    int fused_pdl;       // MAS_FUSED_PDL=0: no programmatic dependent launch
+    int noise_fused;     // MAS_NOISE_FUSED=0: noise-scaled alignment as separate launches
+    int stage;           // MAS_STAGE: 1 = prior preparation only, 2 = skip it (reuse the images in the workspace);
+                         // bench.py times the prior kernel alone with it
+    int tc_debug, dp_debug, tc_no_tma, tc_grid, tc_pair, trace;   // trace build only (MAS_TC_DEBUG, MAS_DP_DEBUG, ...)
+};
+const Config &config();
 
 #define MAS_CUDA_TRY(expr)                                        \
     do {                                                          \

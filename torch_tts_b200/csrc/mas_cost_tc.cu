@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(kPriorThreads) mas_prior_images_kernel(const f
     if (live) bias_part[((size_t)b * n_kb + kb) * S + s] = acc1 + acc4;
 }
 
+#ifdef MAS_TRACE
+// single-CTA contraction (cta_group::1): trace build only, for A/B runs against the CTA-pair kernel (MAS_TC_PAIR=0)
 template <bool kStats>
 __global__ void __launch_bounds__(kTcThreads, 1) mas_cost_tc_kernel(const TcParams p,
                                                                     const __grid_constant__ CUtensorMap tm_z,
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_cost_tc_kernel(const TcPara
     extern __shared__ unsigned char smem_raw[];
     cost_tc_role<kStats, false>(p, &tm_z, &tm_out, smem_raw, blockIdx.x, gridDim.x);
 }
+#endif
 
 // CTA-pair version: clusters of 2, one M = 256 cta_group::2 MMA per pair
 template <bool kStats>
@@ -100,12 +103,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-// MAS_TC_PAIR=0 selects the single-CTA (cta_group::1) contraction
-bool cost_tc_pair_enabled()
-{
-    const char *e = getenv("MAS_TC_PAIR");
-    return !(e && *e && atoi(e) == 0);
-}
+// trace build: MAS_TC_PAIR=0 selects the single-CTA (cta_group::1) contraction
+bool cost_tc_pair_enabled() { return !kTrace || config().tc_pair != 0; }
 
 bool cost_tc_supported(int B, int D, int T, int S)
 {
@@ -123,15 +122,15 @@ size_t cost_tc_workspace_bytes(int B, int D, int T, int S)
 
 int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out,
                     double *stats_out, const int32_t *t_ys, void *workspace, size_t workspace_bytes, int B, int D, int T,
-                    int S, uint32_t *flags_to_clear, int n_flags, cudaStream_t stream)
+                    int S, uint32_t *flags_to_clear, int n_flags, cudaStream_t stream, int ld)
 {
+    if (ld <= 0) ld = S;
     if (!workspace || workspace_bytes < cost_tc_workspace_bytes(B, D, T, S)) return MAS_ERR_WORKSPACE;
     const int n_kb = (D + kDPerKb - 1) / kDPerKb, n_blocks = (S + kNMax - 1) / kNMax;
     unsigned char *images = static_cast<unsigned char *>(workspace);
     float *bias = reinterpret_cast<float *>(images + align_up((size_t)B * n_blocks * n_kb * 2 * kBPart, 256));
     if (stats_out) MAS_CUDA_TRY(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double), stream));
-    const char *dbg = getenv("MAS_TC_DEBUG");  // bit 16: reuse the images already in the workspace (timing experiments)
-    if (!(dbg && *dbg && (atoi(dbg) & 16))) {
+    if (config().stage != 2) {   // MAS_STAGE=2: reuse the images already in the workspace (timing experiments)
         mas_prior_images_kernel<<<dim3(n_kb, B, n_blocks * kPriorParts), kPriorThreads, 0, stream>>>(m_p, logs_p, images, bias, D, S, n_kb,
                                                                      flags_to_clear, n_flags);
         note_launch();
@@ -156,16 +155,15 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
     p.wave = B;
     p.seq_k = 1 << 28;
     p.seq_pure0 = 0;
+    p.ld = ld;
     p.trace = trace_buffer();
-    const char *e = getenv("MAS_TC_DEBUG");
-    p.debug = (e && *e) ? atoi(e) : 0;
-    const char *nt = getenv("MAS_TC_NO_TMA");  // A-B experiments: bit 1 plain z loads, bit 2 plain output stores
-    const int no_tma = (nt && *nt) ? atoi(nt) : 0;
-    // tensor maps: z_p as [B][D][T] with a [1][16][128] box, neg_cent as [B][T][S] with a swizzled [1][32][32] box
+    p.debug = config().tc_debug;
+    const int no_tma = config().tc_no_tma;  // trace build, A-B experiments: bit 1 plain z loads, bit 2 plain output stores
+    // tensor maps: z_p as [B][D][T] with a [1][16][128] box, neg_cent as [B][T][ld] with a swizzled [1][32][32] box
     p.z_tma = !(no_tma & 1) && make_tmap_f32_3d(&plan.tm_z, z_p, (uint64_t)T, (uint64_t)D, (uint64_t)B, (uint64_t)T * 4,
                                                 (uint64_t)D * T * 4, kBM, kDPerKb, 1, false);
-    p.out_tma = !(no_tma & 2) && make_tmap_f32_3d(&plan.tm_out, neg_cent_out, (uint64_t)S, (uint64_t)T, (uint64_t)B,
-                                                  (uint64_t)S * 4, (uint64_t)T * S * 4, 32, 32, 1, true);
+    p.out_tma = !(no_tma & 2) && make_tmap_f32_3d(&plan.tm_out, neg_cent_out, (uint64_t)ld, (uint64_t)T, (uint64_t)B,
+                                                  (uint64_t)ld * 4, (uint64_t)T * ld * 4, 32, 32, 1, true);
     return MAS_OK;
 }
 
@@ -181,10 +179,12 @@ int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, floa
     int dev = 0, sms = 148;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     if (dev != configured_dev) {
+#ifdef MAS_TRACE
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_cost_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kTcSmem));
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_cost_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kTcSmem));
+#endif
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_cost_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kTcSmem));
         MAS_CUDA_TRY(cudaFuncSetAttribute(mas_cost_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -192,9 +192,8 @@ int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, floa
         configured_dev = dev;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char *g = getenv("MAS_TC_GRID");  // experiments: restrict the contraction to fewer SMs
-    if (g && *g && atoi(g) > 0 && atoi(g) < sms) sms = atoi(g);
-    if (plan.p.debug & 8) return MAS_OK;  // timing experiments: prior preparation only
+    if (config().tc_grid > 0 && config().tc_grid < sms) sms = config().tc_grid;  // trace build: fewer SMs
+    if (config().stage == 1) return MAS_OK;  // MAS_STAGE=1: prior preparation only (bench.py times it alone)
     if (cost_tc_pair_enabled()) {
         const int n_units = B * ((plan.p.m_tiles + 1) / 2) * plan.p.n_blocks;
         int grid = 2 * n_units < sms ? 2 * n_units : (sms & ~1);
@@ -203,12 +202,14 @@ int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, floa
         else
             mas_cost_tc_pair_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
     } else {
+#ifdef MAS_TRACE
         const int n_tiles = B * plan.p.m_tiles * plan.p.n_blocks;
         const int grid = n_tiles < sms ? n_tiles : sms;
         if (stats_out)
             mas_cost_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
         else
             mas_cost_tc_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(plan.p, plan.tm_z, plan.tm_out);
+#endif
     }
     note_launch();
     MAS_CUDA_TRY(cudaGetLastError());

@@ -222,7 +222,8 @@ struct TcParams {
     const float *z_p;
     const unsigned char *images;   // [B][n_blocks][n_kb][2 parts][kBPart]
     const float *bias_part;        // [B][n_kb][S]
-    float *out;                    // [B][T][S]
+    float *out;                    // [B][T][ld]
+    int ld;                        // row stride of `out` in floats: S, or S rounded up to 4 (private plane; pad columns get 0)
     double *stats;                 // nullable
     const int32_t *t_ys;           // nullable: skip mel tiles entirely past t_y (no noise statistics then)
     uint32_t *flags;               // nullable: [B][m_tiles], set to 1 (release) when a tile is in memory
@@ -363,7 +364,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     };
     // diagnostics: trace[16384 + cta * 64 + role * 16 + 2 * unit + {0: begin, 1: end}], roles 0 MMA, 1 epilogue, 2 converter, 3 z
     auto tr_mark = [&](int role, uint32_t unit, int which) {
-        if (p.trace && unit < 8) p.trace[16384 + (size_t)blockIdx.x * 64 + role * 16 + 2 * unit + which] = globaltimer_ns();
+        if (MAS_TR(p) && unit < 8) p.trace[16384 + (size_t)blockIdx.x * 64 + role * 16 + 2 * unit + which] = globaltimer_ns();
     };
 
     if (warp == 0) {
@@ -382,7 +383,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     const unsigned char *img = p.images + ((size_t)(b * p.n_blocks + nb) * p.n_kb + kb) * 2 * kBPart +
                                                (kPair ? rank * b_bytes : 0u);
                     uint64_t *bar = (kPair && rank) ? &bfull[s] : &full[s];
-                    if (p.debug & 64) {  // experiment: no B traffic
+                    if MAS_DBG(p, 64) {  // experiment: no B traffic
                         mbar_arrive(bar);
                         continue;
                     }
@@ -394,7 +395,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
         }
     } else if (warp == 3) {
         // ======================= raw z producer (runs ahead of the operand ring) =======================
-        if (lane == 0 && p.z_tma && !(p.debug & 32)) {
+        if (lane == 0 && p.z_tma && !MAS_DBG(p, 32)) {
             uint32_t it = 0;
             for (int un = 0, i = unit_index(0); i >= 0; i = unit_index(++un)) {
                 int b, mt, nb;
@@ -435,7 +436,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     const uint64_t b_hi = make_desc_sw64(st + 2 * kAPart),
                                    b_lo = make_desc_sw64(st + 2 * kAPart + Cfg::kBPartS);
 #pragma unroll
-                    for (int k = 0; k < kBK / 16 && !(p.debug & 4); ++k) {
+                    for (int k = 0; k < kBK / 16 && !MAS_DBG(p, 4); ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 16 bf16 = 32 bytes along K
                         if (kPair) {
                             umma_bf16_2cta(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
@@ -534,7 +535,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 pub_cnt[par] = 0u;
                 __threadfence();
                 st_release_gpu(flag, 1u);
-                if (p.trace) {
+                if (MAS_TR(p)) {
                     unsigned long long *tr = p.trace + (size_t)blockIdx.x * 64;
                     const unsigned long long n = tr[0] + 1;   // word 0: count, then one time per published tile
                     tr[0] = n;
@@ -554,7 +555,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             if (tid == 128) tr_mark(1, nt, 0);
             const int t = mt * kBM + row;
             const int c_base = nb * kNMax, ncols = block_cols(nb), s_left = p.S - c_base;
-            float *orow = p.out + ((size_t)b * p.T + t) * p.S + c_base;
+            float *orow = p.out + ((size_t)b * p.T + t) * p.ld + c_base;
             const uint32_t taddr = tmem_base + a * kNMax + ((uint32_t)(wq * 32) << 16);
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t r[32];
@@ -601,7 +602,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                         ssq += sdd64 + 2.0 * cd * sd64 + nd * cd * cd;
                     }
                 }
-                if (p.debug & 2) continue;
+                if MAS_DBG(p, 2) continue;
                 if (p.out_tma) {
                     unsigned char *buf = ebuf + (nst & 1u) * kEpiBufBytes;
                     if (lane == 0) bulk_wait_read<1>();  // the store that last read this buffer is done with it
@@ -640,8 +641,8 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     mbar_arrive(&acc_empty[a]);
                 if (p.flags && mt < p.m_tiles) {
                     uint32_t *flag = p.flags + (size_t)b * p.m_tiles + mt;
-                    if (p.out_tma && !(p.debug & 2)) {
-                        if (p.debug & 64) {
+                    if (p.out_tma && !MAS_DBG(p, 2)) {
+                        if MAS_DBG(p, 64) {
                             pend_flag = flag;  // experiment: publish after the first store of the next unit
                             pend_par = a;
                         } else {
@@ -691,21 +692,21 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
                 if (tid == 256 && kb == p.n_kb - 2) tr_mark(2, it / (uint32_t)p.n_kb, 1);
                 if ((int)(it & 1u) != grp) continue;
-                const long long c0k = p.trace ? clock64() : 0;
+                const long long c0k = MAS_TR(p) ? clock64() : 0;
                 long long c1k = 0, c2k = 0, c3k = 0, c4k = 0;
                 float zc[kDPerKb];
-                if (p.debug & 32) {  // experiment: no z traffic
+                if MAS_DBG(p, 32) {  // experiment: no z traffic
 #pragma unroll
                     for (int d = 0; d < kDPerKb; ++d) zc[d] = 0.f;
                 } else if (p.z_tma) {
                     const uint32_t zs = it % kZStages, zph = (it / kZStages) & 1u;
                     mbar_wait(&zfull[zs], zph);
-                    if (p.trace) c1k = clock64();
+                    if (MAS_TR(p)) c1k = clock64();
                     const float *zr = reinterpret_cast<const float *>(smem + Cfg::kOffZ + zs * kZStageBytes) + row;
 #pragma unroll
                     for (int d = 0; d < kDPerKb; ++d) zc[d] = zr[d * kBM];  // zero-filled past T / D by the TMA
                     __syncwarp();
-                    if (p.trace) c2k = clock64() + (long long)(__float_as_int(zc[0]) & 0);
+                    if (MAS_TR(p)) c2k = clock64() + (long long)(__float_as_int(zc[0]) & 0);
                     if (lane == 0) mbar_arrive(&zempty[zs]);
                 } else {
                     const int d0 = kb * kDPerKb;
@@ -714,7 +715,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 }
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
-                if (p.trace) c3k = clock64();
+                if (MAS_TR(p)) c3k = clock64();
                 unsigned char *a_hi = smem + s * Cfg::kStage;
                 unsigned char *a_lo = a_hi + kAPart;
 #pragma unroll
@@ -731,12 +732,12 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                         split2(x0, x1, hi[j], lo[j]);
                     }
                     const uint32_t off = sw64_offset(row, c * 8);
-                    if (!(p.debug & 1)) {
+                    if (!MAS_DBG(p, 1)) {
                         *reinterpret_cast<uint4 *>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
-                if (p.trace) c4k = clock64();
+                if (MAS_TR(p)) c4k = clock64();
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) {
@@ -745,14 +746,14 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     else
                         mbar_arrive(&full[s]);
                 }
-                if (p.trace) {
+                if (MAS_TR(p)) {
                     const long long c5k = clock64();
                     ph_acc[0] += c1k - c0k, ph_acc[1] += c2k - c1k, ph_acc[2] += c3k - c2k, ph_acc[3] += c4k - c3k,
                         ph_acc[4] += c5k - c4k;
                 }
             }
         }
-        if (p.trace && (tid == 256 || tid == 384))
+        if (MAS_TR(p) && (tid == 256 || tid == 384))
             for (int j = 0; j < 5; ++j)
                 p.trace[32768 + (size_t)blockIdx.x * 16 + (tid == 384 ? 8 : 0) + j] = (unsigned long long)ph_acc[j];
     }
@@ -780,6 +781,6 @@ size_t cost_tc_workspace_bytes(int B, int D, int T, int S);
 // and fills `plan` for the contraction
 int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out,
                     double *stats_out, const int32_t *t_ys, void *workspace, size_t workspace_bytes, int B, int D, int T,
-                    int S, uint32_t *flags_to_clear, int n_flags, cudaStream_t stream);
+                    int S, uint32_t *flags_to_clear, int n_flags, cudaStream_t stream, int ld = 0);
 
 }  // namespace mas

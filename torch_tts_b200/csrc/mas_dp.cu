@@ -4,17 +4,11 @@
 
 namespace mas {
 
-static int env_int(const char *name, int dflt)
-{
-    const char *s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
-
 // ---------------------------------------------------------------------------
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
-bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool bits_smem, bool hop_smem, size_t budget,
-                 bool with_noise, bool vk)
+bool dp_plan_try(DpPlan &pl, int T, int S, int ld, int W, int C, int R, int stages, bool bits_smem, bool hop_smem,
+                 size_t budget, bool with_noise, bool vk)
 {
     const int S_pad = W * 32 * C;
     const int n_blk = (T + kCheck - 1) / kCheck;  // 32-row blocks of decision words
@@ -31,7 +25,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
     if (bits_smem) off += align_up((size_t)n_blk * (S_pad + kBitsPad) * 4, 16);
     p.off_hop = (uint32_t)off;
     if (hop_smem) off += align_up((size_t)hop_rows * S_pad, 16);
-    p.stage_bytes = (uint32_t)align_up((size_t)R * S * 4 + 16 + 64, 128);  // tile + misalignment + zeroed pad
+    p.stage_bytes = (uint32_t)align_up((size_t)R * ld * 4 + 16 + 64, 128);  // tile + misalignment + zeroed pad
     p.noise_off = with_noise ? p.stage_bytes : 0;                          // the noise tile follows the cost tile
     if (with_noise) p.stage_bytes *= 2;
     off = align_up(off, 128);
@@ -67,11 +61,12 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int W, int C, int R, int stages, bool
 int dp_team_warps(int S)
 {
     int W = S <= 512 ? 2 : 4;
-    if (env_int("MAS_DP_WARPS", 0) == 4 && S > 128 && S <= 256) W = 4;  // experiments: 4 warps x 2 columns per thread
+    if (config().dp_warps == 4 && S > 128 && S <= 256) W = 4;  // 4 warps x 2 columns per thread
     return W;
 }
 
-bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, size_t budget, bool with_noise, bool vk)
+bool dp_make_plan(DpPlan &pl, int B, int T, int S, int ld, int stages_hint, int R_hint, size_t budget, bool with_noise,
+                  bool vk)
 {
     const int W = dp_team_warps(S);
     const int C = (S + W * 32 - 1) / (W * 32);
@@ -83,7 +78,7 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, 
     bool ok = false;
     if (vk) {
         // warp split: everything on chip, one tile of prefetch distance at least, or not at all
-        for (int st = 5; st >= W + 1 && !ok; --st) ok = dp_plan_try(pl, T, S, W, C, R0, st, true, true, budget, false, true);
+        for (int st = 5; st >= W + 1 && !ok; --st) ok = dp_plan_try(pl, T, S, ld, W, C, R0, st, true, true, budget, false, true);
         if (!ok) return false;
         pl.ws_bits_bytes = pl.ws_hop_bytes = 0;
         return true;
@@ -95,7 +90,7 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, 
         const int min_stages = (mode == 2) ? W + 1 : W + 2;
         for (int R = (mode == 2 && R_hint <= 0 && R0 < 32) ? 2 * R0 : R0; R >= R0 && !ok; R /= 2)
             for (int st = (stages_hint > 0 ? stages_hint : 6); st >= min_stages && !ok; --st) {
-                ok = dp_plan_try(pl, T, S, W, C, R, st, bits_smem, hop_smem, budget, with_noise, false);
+                ok = dp_plan_try(pl, T, S, ld, W, C, R, st, bits_smem, hop_smem, budget, with_noise, false);
                 if (stages_hint > 0) break;
             }
     }
@@ -105,11 +100,11 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int stages_hint, int R_hint, 
         // (noise-scaled MAS at S = 256: three 66 KB stages leave room for the 9 KB of hop bytes, not for the
         // 32 KB of decision words).
         DpPlan alt = pl;
-        if (dp_plan_try(alt, T, S, W, C, pl.p.R, pl.p.stages, false, true, budget, with_noise, false)) pl = alt;
+        if (dp_plan_try(alt, T, S, ld, W, C, pl.p.R, pl.p.stages, false, true, budget, with_noise, false)) pl = alt;
     }
     if (!ok) {
         // last resort: no prefetch distance at all
-        ok = dp_plan_try(pl, T, S, W, C, R0, W, false, false, budget, with_noise, false);
+        ok = dp_plan_try(pl, T, S, ld, W, C, R0, W, false, false, budget, with_noise, false);
     }
     if (!ok) return false;
     pl.ws_bits_bytes = pl.p.bits_in_smem ? 0 : (size_t)B * pl.p.bits_words_per_cta * 4;
@@ -197,10 +192,12 @@ size_t dp_workspace_bytes(int B, int T, int S)
 {
     // the larger of the plans without / with a noise tile per stage (fewer stages may move the bits off chip)
     size_t bits = 0, hop = 0;
-    for (int noise = 0; noise < 2; ++noise) {
+    for (int variant = 0; variant < 4; ++variant) {
+        const bool noise = (variant & 1) != 0;
+        const int ld = (variant & 2) ? ((S + 3) & ~3) : S;   // caller's plane / the fused kernel's padded private plane
         DpPlan pl{};
-        if (!dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), 0, kSmemBudget, noise != 0, false)) {
-            if (!noise) return 0;
+        if (!dp_make_plan(pl, B, T, S, ld, config().dp_stages, 0, kSmemBudget, noise, false)) {
+            if (variant == 0) return 0;
             continue;
         }
         bits = pl.ws_bits_bytes > bits ? pl.ws_bits_bytes : bits;
@@ -230,7 +227,7 @@ template <int C, int R, int W>
 static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
 {
     // vector cost loads need every tile row 16-byte aligned in shared memory
-    const bool vec = (pl.p.S % 4 == 0) && ((reinterpret_cast<uintptr_t>(pl.p.neg_cent) & 15) == 0);
+    const bool vec = (pl.p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(pl.p.neg_cent) & 15) == 0);
     if (pl.p.noise) {
         // noise applied while the cost streams in: vector path only (dp_noise_supported)
         if (!vec || (reinterpret_cast<uintptr_t>(pl.p.noise) & 15)) return MAS_ERR_UNSUPPORTED_SHAPE;
@@ -238,7 +235,7 @@ static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
     }
     if (pl.p.vk) {
         if (!vec) return MAS_ERR_UNSUPPORTED_SHAPE;
-        if constexpr (W == 2 && R == 32)
+        if constexpr (((W == 2 && C <= 4) || (W == 4 && C == 2)) && R == 32)
             return launch_dp_cv<C, R, W, true, false, true>(pl, stream);
         else
             return MAS_ERR_UNSUPPORTED_SHAPE;
@@ -251,16 +248,18 @@ static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
                size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget,
-               bool with_noise)
+               bool with_noise, int ld)
 {
     pl = DpPlan{};
+    if (ld <= 0) ld = S;   // cost rows packed like the caller's [B,T,S] tensor
     // value / origin warp split (MAS_DP_VK=0 turns it off): W value warps run the recursion and leave the decision
     // words, W origin warps one step behind replay them into origins / hops / checkpoints.  S <= 256 with 16-byte
     // rows, no noise, everything on chip; other shapes keep the single-role warps.
-    bool vk = env_int("MAS_DP_VK", 1) && !with_noise && R == 0 && S <= 256 && S % 4 == 0 &&
-              (reinterpret_cast<uintptr_t>(neg_cent) & 15) == 0 && dp_team_warps(S) == 2 && dp_chunk_rows(S) == 32;
-    if (vk) vk = dp_make_plan(pl, B, T, S, 0, 0, smem_budget ? smem_budget : (size_t)kSmemBudget, false, true);
-    if (!vk && !dp_make_plan(pl, B, T, S, env_int("MAS_DP_STAGES", 0), R,
+    bool vk = config().dp_vk && !with_noise && R == 0 && S <= 256 && ld % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(neg_cent) & 15) == 0 && dp_chunk_rows(S) == 32 &&
+              (dp_team_warps(S) == 2 || (S + 127) / 128 == 2);   // 4 value warps: C = 2 columns per thread only
+    if (vk) vk = dp_make_plan(pl, B, T, S, ld, 0, 0, smem_budget ? smem_budget : (size_t)kSmemBudget, false, true);
+    if (!vk && !dp_make_plan(pl, B, T, S, ld, config().dp_stages, R,
                              smem_budget ? smem_budget : (size_t)kSmemBudget, with_noise, false))
         return MAS_ERR_UNSUPPORTED_SHAPE;
     const size_t need = dp_workspace_bytes(B, T, S);
@@ -282,11 +281,12 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
     p.zero_flags = nullptr;
     p.zero_queue = nullptr;
     p.trace = trace_buffer();
-    p.debug = env_int("MAS_DP_DEBUG", 0);
+    p.debug = config().dp_debug;
     p.order = nullptr;
     p.B = B;
     p.T = T;
     p.S = S;
+    p.ld = ld;
     p.path_dtype = path_dtype;
     if (order_out) *order_out = reinterpret_cast<int32_t *>(ws);
     ws += align_up((size_t)B * 4, 256);

@@ -58,7 +58,7 @@ struct DpParams {
     const int32_t *t_ys;
     const int32_t *t_xs;
     const int32_t *order;  // nullable: CTA -> utterance (longest first)
-    unsigned char *path;
+    unsigned char *path;    // nullable: compact outputs only (no zero fill, no scatter of ones)
     int32_t *dur;
     int32_t *idx;
     int32_t *status;
@@ -71,6 +71,7 @@ struct DpParams {
     uint32_t *bits_ws;      // global spill (per CTA region), used when !bits_in_smem
     unsigned char *hop_ws;  // global spill (per CTA region), used when !hop_in_smem
     int B, T, S;
+    int ld;      // row stride of neg_cent in floats (S, or S rounded up to 4 for the fused kernel's private plane)
     int R;       // mel rows per chunk (template parameter of the role; 32, 16 or 8)
     int W;       // DP warps per team (template parameter of the role; 2 or 4)
     int vk;      // value / origin warp split (W value warps + W origin warps + producer)
@@ -135,7 +136,7 @@ struct DpNoise {
 //   kOrg    false: no origin tracking here (warp split: the origin warps rebuild it from the decision words)
 template <int C, int NR, bool kEdge, bool kVec, bool kExact, bool kNoise, bool kOrg = true>
 __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *trow,
-                                        int S, int bit0, float &carry_v, int &carry_o, const float *bin_v,
+                                        int ld, int bit0, float &carry_v, int &carry_o, const float *bin_v,
                                         const int *bin_o, float *bout_v, int *bout_o, int y, int x0, bool lane0,
                                         bool lane31, const DpNoise &nz)
 {
@@ -147,7 +148,7 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
     // ---- all loads for the NR rows up front
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-        const float *src = trow + (size_t)i * S;
+        const float *src = trow + (size_t)i * ld;
         if (kVec && (C % 4 == 0)) {
 #pragma unroll
             for (int k = 0; k < C; k += 4) {
@@ -270,15 +271,15 @@ __device__ __forceinline__ void dp_rows(float (&v)[C], int (&org)[C], float &fin
 // one chunk (<= R rows) of this warp's columns; bin/bout point at the ring slot of the chunk's first row
 template <int C, int R, bool kEdge, bool kVec, bool kExact, bool kNoise, bool kOrg = true>
 __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fin, uint32_t (&wl)[C], const float *tile,
-                                         int S, int rows, int row0, float &carry_v, int &carry_o, const float *bin_v,
+                                         int S, int ld, int rows, int row0, float &carry_v, int &carry_o, const float *bin_v,
                                          const int *bin_o, float *bout_v, int *bout_o, int x0, bool lane0, bool lane31,
                                          const DpNoise &nz)
 {
-    // Threads whose columns lie past S re-read the last real columns instead of whatever
-    // follows the row: their results are never used, but they must not invent NaNs.
-    // (A thread straddling S reads at most C-1 floats of the next row, or of the zeroed
-    // pad the producer keeps behind every tile.)
-    const float *trow = tile + (x0 < S ? x0 : S - C);
+    // Threads whose columns lie past the row (ld = S, or S rounded up to 4 with zeros in the pad columns) re-read
+    // its last C columns instead of whatever follows: their results are never used, but they must not invent
+    // NaNs.  (A thread straddling ld reads at most C-1 floats of the next row, or of the zeroed pad the
+    // producer keeps behind every tile.)
+    const float *trow = tile + (x0 < ld ? x0 : ld - C);
     // 8 rows per trip: small enough to stay in the instruction cache (a fully unrolled 32-row body is
     // ~10 KB per variant and its cold fetch cost more than the rows themselves), large enough that the
     // decision bits are still set with immediates; the 8-bit group is merged into the chunk word per trip.
@@ -288,9 +289,9 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
         uint32_t w8[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) w8[k] = 0u;
-        dp_rows<C, 4, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
+        dp_rows<C, 4, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)r * ld, ld, 0, carry_v, carry_o, bin_v + r,
                                            bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31, nz);
-        dp_rows<C, 4, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)(r + 4) * S, S, 4, carry_v, carry_o,
+        dp_rows<C, 4, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)(r + 4) * ld, ld, 4, carry_v, carry_o,
                                            bin_v + r + 4, bin_o + r + 4, bout_v + r + 4, bout_o + r + 4, row0 + r + 4, x0,
                                            lane0, lane31, nz);
 #pragma unroll
@@ -301,7 +302,7 @@ __device__ __forceinline__ void dp_chunk(float (&v)[C], int (&org)[C], float &fi
         uint32_t w8[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) w8[k] = 0u;
-        dp_rows<C, 1, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)r * S, S, 0, carry_v, carry_o, bin_v + r,
+        dp_rows<C, 1, kEdge, kVec, kExact, kNoise, kOrg>(v, org, fin, w8, trow + (size_t)r * ld, ld, 0, carry_v, carry_o, bin_v + r,
                                            bin_o + r, bout_v + r, bout_o + r, row0 + r, x0, lane0, lane31, nz);
 #pragma unroll
         for (int k = 0; k < C; ++k) wl[k] |= w8[k] << r;
@@ -409,7 +410,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
 {
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int T = p.T, S = p.S;
+    const int T = p.T, S = p.S, ld = p.ld;
     const int t_y = p.t_ys[b], t_x = p.t_xs[b];
     constexpr int S_pad = W * 32 * C;
     constexpr int S_bits = S_pad + kBitsPad;
@@ -419,11 +420,11 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     constexpr int kProducerWarp = kVK ? 2 * W : W;
     const int esize = path_elem_size(p.path_dtype);
     const size_t plane = (size_t)T * S;
-    unsigned char *path_b = p.path + (size_t)b * plane * esize;
+    unsigned char *path_b = p.path ? p.path + (size_t)b * plane * esize : nullptr;
 
     // ---- length contract (anything else is UB in the reference) ----
     if (!(t_x >= 1 && t_x <= t_y && t_y <= T && t_x <= S)) {
-        {
+        if (path_b) {
             const size_t total = plane * esize;
             const size_t seg = align_up((total + kThreads / 32 - 1) / (kThreads / 32), 512);
             size_t lo = (size_t)warp * seg, hi = lo + seg;
@@ -474,11 +475,11 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     if (tid == 0) *nonfinite_s = 0;
     bar_sync(bar, kThreads);  // previous utterance's backtrack is done with the shared buffers
 
-    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 0] = globaltimer_ns();
+    if (MAS_TR(p) && tid == 0) p.trace[12288 + (size_t)b * 32 + 0] = globaltimer_ns();
     const int n_chunks = (t_y + R - 1) / R;
     const int n_steps = n_chunks + kDpWarps - 1 + (kVK ? 1 : 0);  // the bookkeeping warps trail by one step
-    const size_t utt_elem0 = (size_t)b * plane;  // first element of this utterance's cost plane
-    const size_t total_bytes = (size_t)p.B * plane * 4;
+    const size_t utt_elem0 = (size_t)b * T * ld;  // first element of this utterance's cost plane
+    const size_t total_bytes = (size_t)p.B * T * ld * 4;
 
     // Pass 0 runs the short-chain body; only if it met a non-finite cost does pass 1 redo the
     // forward DP with the reference's exact compare-select (NaN/Inf semantics of core.pyx).
@@ -498,13 +499,13 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     uint32_t *f = p.flags + (size_t)b * p.flag_tiles + (row0 >> 7);
                     while (ld_acquire_gpu(f) == 0u) __nanosleep(64);
                     *f = 0u;
-                    if (p.trace) p.trace[12288 + (size_t)b * 32 + 2 + (row0 >> 7)] = globaltimer_ns();
+                    if (MAS_TR(p)) p.trace[12288 + (size_t)b * 32 + 2 + (row0 >> 7)] = globaltimer_ns();
                     fence_proxy_async_all();  // order the bulk (async-proxy) reads below after the acquire
                 }
-                const size_t start = (utt_elem0 + (size_t)row0 * S) * 4;
+                const size_t start = (utt_elem0 + (size_t)row0 * ld) * 4;
                 const uint32_t mis = (uint32_t)(start & 15);
                 const size_t src0 = start - mis;
-                const uint32_t want = mis + (uint32_t)rows * S * 4;
+                const uint32_t want = mis + (uint32_t)rows * ld * 4;
                 uint32_t bulk = (want + 15u) & ~15u;
                 unsigned char *dst = smem + p.off_stage + (size_t)st * p.stage_bytes;
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(p.neg_cent) + src0;
@@ -518,7 +519,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         *reinterpret_cast<float *>(dst + o) =
                             (o < want) ? *reinterpret_cast<const float *>(src + o) : 0.0f;
                 }
-                if (p.debug & 4) bulk = 0;
+                if MAS_DBG(p, 4) bulk = 0;
                 if (kNoise) {
                     // the noise tile of the same cells, nz_off behind the cost tile (same padding / tail rules)
                     unsigned char *ndst = dst + p.noise_off;
@@ -543,12 +544,12 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             }
             // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
             // zeroed shared buffer when the plane is 16-byte aligned, plain stores otherwise
-            const size_t pbytes = (pass == 0 && !(p.debug & 1) && !p.zero_flags) ? plane * esize : 0;
+            const size_t pbytes = (pass == 0 && !MAS_DBG(p, 1) && !p.zero_flags && path_b) ? plane * esize : 0;
             const bool bulk_ok = ((reinterpret_cast<uintptr_t>(path_b) | pbytes) & 15) == 0;
             const size_t quota = align_up((pbytes + n_steps - 1) / n_steps, 512);
             long long pacc[3] = {0, 0, 0};  // diagnostics: cycles in zero-fill issue, barrier, tile issue
             for (int step = 0; step < n_steps; ++step) {
-                const long long q0 = p.trace ? clock64() : 0;
+                const long long q0 = MAS_TR(p) ? clock64() : 0;
                 size_t lo = (size_t)step * quota, hi = lo + quota;
                 if (lo > pbytes) lo = pbytes;
                 if (hi > pbytes || step == n_steps - 1) hi = pbytes;
@@ -563,17 +564,17 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         zero_bytes_warp(path_b + lo, hi - lo, lane);
                     }
                 }
-                const long long q1 = p.trace ? clock64() : 0;
+                const long long q1 = MAS_TR(p) ? clock64() : 0;
                 bar_sync(bar, kThreads);
-                const long long q2 = p.trace ? clock64() : 0;
+                const long long q2 = MAS_TR(p) ? clock64() : 0;
                 const int freed = step - (kDpWarps - 1);
                 if (lane == 0 && freed >= 0 && freed + (int)n_stages < n_chunks) issue_tile(freed + (int)n_stages);
-                if (p.trace) {
+                if (MAS_TR(p)) {
                     const long long q3 = clock64();
                     pacc[0] += q1 - q0, pacc[1] += q2 - q1, pacc[2] += q3 - q2;
                 }
             }
-            if (p.trace && lane == 0)
+            if (MAS_TR(p) && lane == 0)
                 for (int j = 0; j < 3; ++j) p.trace[40960 + (size_t)b * 16 + 8 + j] = (unsigned long long)pacc[j];
             if (pass == 0 && bulk_ok && lane == 0) bulk_wait_all();  // zeros land before the ones are scattered
         } else if (kVK && warp >= W) {
@@ -593,9 +594,9 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             long long kacc[2] = {0, 0};  // diagnostics: cycles in compute, barrier
             for (int step = 0; step < n_steps; ++step) {
                 const int c = step - w - 1;
-                const long long f0 = p.trace ? clock64() : 0;
+                const long long f0 = MAS_TR(p) ? clock64() : 0;
                 long long f1 = f0;
-                if (c >= 0 && c < n_chunks && !(p.debug & 16)) {
+                if (c >= 0 && c < n_chunks && !MAS_DBG(p, 16)) {
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
                     const int slot0 = (c & 1) * R;
@@ -617,15 +618,15 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         }
                         if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
                     }
-                    if (p.trace) f1 = clock64() + (long long)(org[0] & 0);
+                    if (MAS_TR(p)) f1 = clock64() + (long long)(org[0] & 0);
                 }
                 bar_sync(bar, kThreads);
-                if (p.trace) {
+                if (MAS_TR(p)) {
                     const long long f2 = clock64();
                     kacc[0] += f1 - f0, kacc[1] += f2 - f1;
                 }
             }
-            if (p.trace && lane == 0 && w == 0)
+            if (MAS_TR(p) && lane == 0 && w == 0)
                 for (int j = 0; j < 2; ++j) p.trace[40960 + (size_t)b * 16 + 4 + j] = (unsigned long long)kacc[j];
 #pragma unroll
             for (int k = 0; k < C; ++k) hop[x0 + k] = (unsigned char)(x0 + k - org[k]);
@@ -656,22 +657,22 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             uint32_t st = g0 % n_stages, st_par = (g0 / n_stages) & 1u;  // stage / mbarrier parity of chunk 0, then stepped
             for (int step = 0; step < n_steps; ++step) {
                 const int c = step - w;
-                long long d0 = p.trace ? clock64() : 0, d1 = d0, d2 = d0, d3 = d0;
+                long long d0 = MAS_TR(p) ? clock64() : 0, d1 = d0, d2 = d0, d3 = d0;
                 if (c >= 0 && c < n_chunks) {
                     const int row0 = c * R;
                     const int rows = min(R, t_y - row0);
                     const int slot0 = (c & 1) * R;
-                    const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * S) * 4) & 15);
+                    const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * ld) * 4) & 15);
                     const float *tile =
                         reinterpret_cast<const float *>(smem + p.off_stage + (size_t)st * p.stage_bytes + mis);
                     mbar_wait(&full[st], st_par);
-                    if (p.trace) d1 = clock64();
+                    if (MAS_TR(p)) d1 = clock64();
                     const bool edge = row0 < edge_rows;
 #define MAS_CHUNK(EDGE, EXACT)                                                                             \
-    dp_chunk<C, R, EDGE, kVec, EXACT, kNoise, !kVK>(v, org, fin, wl, tile, S, rows, row0, carry_v, carry_o,        \
+    dp_chunk<C, R, EDGE, kVec, EXACT, kNoise, !kVK>(v, org, fin, wl, tile, S, ld, rows, row0, carry_v, carry_o,    \
                                                     bin_v + slot0, bin_o + slot0, bout_v + slot0, bout_o + slot0, \
                                                     x0, lane0, lane31, nzp)
-                    if (p.debug & 2) {
+                    if MAS_DBG(p, 2) {
                     } else if (pass == 0) {
                         if (edge)
                             MAS_CHUNK(true, false);
@@ -684,7 +685,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                             MAS_CHUNK(false, true);
                     }
 #undef MAS_CHUNK
-                    if (p.trace) d2 = clock64() + (long long)(__float_as_int(v[0]) & 0);
+                    if (MAS_TR(p)) d2 = clock64() + (long long)(__float_as_int(v[0]) & 0);
                     // decision words: R < 32 accumulates 32 / R chunks per word
                     const int end_row = row0 + rows;
                     const bool word_done = ((end_row & (kCheck - 1)) == 0) || (c == n_chunks - 1);
@@ -726,16 +727,16 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                         // the right-hand warp must see the restarted origin of our last column
                         if (lane31) bout_o[slot0 + rows - 1] = x0 + C - 1;
                     }
-                    if (p.trace) d3 = clock64();
+                    if (MAS_TR(p)) d3 = clock64();
                     if (++st == n_stages) st = 0, st_par ^= 1u;
                 }
                 bar_sync(bar, kThreads);
-                if (p.trace) {
+                if (MAS_TR(p)) {
                     const long long d4 = clock64();
                     dacc[0] += d1 - d0, dacc[1] += d2 - d1, dacc[2] += d3 - d2, dacc[3] += d4 - d3;
                 }
             }
-            if (p.trace && lane == 0 && (w == 0 || w == 3))
+            if (MAS_TR(p) && lane == 0 && (w == 0 || w == 3))
                 for (int j = 0; j < 4; ++j) p.trace[40960 + (size_t)b * 16 + (w ? 4 : 0) + j] = (unsigned long long)dacc[j];
             // origin of the last row relative to its checkpoint -> hop row 0
             if (!kVK) {
@@ -753,7 +754,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     if (!p.bits_in_smem || !p.hop_in_smem) __threadfence_block();
     bar_sync(bar, kThreads);
 
-    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 1] = globaltimer_ns();
+    if (MAS_TR(p) && tid == 0) p.trace[12288 + (size_t)b * 32 + 1] = globaltimer_ns();
     // =================== backtrack ===================
     const int y_last = t_y - 1;
     const int J = t_y / kCheck;  // checkpoints stored: after rows 31, 63, ..., 32 J - 1
@@ -767,7 +768,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             entry_s[j - 1] = (uint16_t)c;
         }
         idx_s[ix(0)] = 0;
-        if (p.trace) p.trace[12288 + (size_t)b * 32 + 26] = globaltimer_ns();
+        if (MAS_TR(p)) p.trace[12288 + (size_t)b * 32 + 26] = globaltimer_ns();
     }
     bar_sync(bar, kThreads);
     // level 2: independent walks of <= 32 rows, one per thread
@@ -790,27 +791,27 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         }
     }
     for (int x = tid; x < S_pad; x += kThreads) end_s[x] = -1;
-    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 27] = globaltimer_ns();
+    if (MAS_TR(p) && tid == 0) p.trace[12288 + (size_t)b * 32 + 27] = globaltimer_ns();
     if (p.zero_flags && tid == 0) {
         // somebody else zero-fills this utterance's path plane: the ones may only follow the zeros
         uint32_t *f = p.zero_flags + b;
         while (ld_acquire_gpu(f) < (uint32_t)kZeroParts) __nanosleep(64);
         *f = 0u;
     }
-    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 28] = globaltimer_ns();
+    if (MAS_TR(p) && tid == 0) p.trace[12288 + (size_t)b * 32 + 28] = globaltimer_ns();
     bar_sync(bar, kThreads);
 
     // =================== outputs ===================
     for (int y = tid; y < t_y; y += kThreads) {
         const int c = idx_s[ix(y)];
-        store_one(path_b, (size_t)y * S + c, p.path_dtype);
+        if (path_b) store_one(path_b, (size_t)y * S + c, p.path_dtype);
         if (y == y_last || idx_s[ix(y + 1)] != c) end_s[c] = y;
     }
     if (p.idx) {
         for (int y = tid; y < T; y += kThreads) p.idx[(size_t)b * T + y] = (y < t_y) ? (int)idx_s[ix(y)] : -1;
     }
     if (p.status && tid == 0) p.status[b] = MAS_UTT_OK;
-    if (p.trace && tid == 0) p.trace[12288 + (size_t)b * 32 + 30] = globaltimer_ns();
+    if (MAS_TR(p) && tid == 0) p.trace[12288 + (size_t)b * 32 + 30] = globaltimer_ns();
     if (p.dur) {
         bar_sync(bar, kThreads);
         for (int x = tid; x < S; x += kThreads) {
@@ -899,6 +900,6 @@ size_t dp_workspace_bytes(int B, int T, int S);
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
                size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget,
-               bool with_noise = false);
+               bool with_noise = false, int ld = 0);
 
 }  // namespace mas

@@ -180,49 +180,58 @@ __global__ void mas_logw_kernel(const int32_t *__restrict__ dur, const int32_t *
 
 // inference side (commons.generate_path, commons.py:130-145): durations -> alignment.
 // The reference builds the dense path as sequence_mask(cumsum(duration)) minus its copy shifted by one column,
-// times the mask: cell (y, x) is 1 iff cum[x-1] <= y < cum[x], x < t_x, y < t_y.  Here: the compact form
-// idx[b, y] = that x (or -1), from an integer prefix sum (the durations are ceil()ed floats, exact in fp32 and in
-// int32) and a binary search per frame; mas_expand_path / mas_expand_prior_f32 take it from there.
+// times the mask: cell (y, x) is 1 iff cum[x-1] <= y < cum[x], x < t_x, y < t_y, with cum the fp32 running sum and
+// y compared as a float.  Here: the compact form idx[b, y] = that x (or -1), from an fp32 prefix sum and a binary
+// search per frame; mas_expand_path / mas_expand_prior_f32 take it from there.
+// Contract: durations finite and >= 0 (negative or NaN entries count as 0).  The running sum saturates at T + 1
+// (every frame index is below it, so larger sums change nothing and Inf / huge values are harmless); for the
+// integer-valued durations of models.py:1303 (ceil) every summation order gives the same exact sums, for
+// fractional ones the scan's association order may differ from torch's in the last ulp (as torch's own CUDA
+// cumsum does from its CPU one).
 // One CTA per utterance.
 __global__ void __launch_bounds__(kScatterThreads) mas_idx_from_durations_kernel(const float *__restrict__ dur_f,
                                                                                  const int32_t *__restrict__ t_xs,
                                                                                  const int32_t *__restrict__ t_ys,
                                                                                  int32_t *__restrict__ idx, int T, int S)
 {
-    __shared__ int cum_s[MAS_MAX_TEXT];
-    __shared__ int warp_tot[kScatterThreads / 32];
+    __shared__ float cum_s[MAS_MAX_TEXT];
+    __shared__ float warp_tot[kScatterThreads / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t_x = min(max(t_xs[b], 0), S);
     const int per = (S + kScatterThreads - 1) / kScatterThreads;
-    int local = 0;
+    const float cap = (float)(T + 1);
+    auto clean = [cap](float d) { return d > 0.0f ? fminf(d, cap) : 0.0f; };   // NaN and negatives -> 0
+    float local = 0.0f;
     for (int j = 0; j < per; ++j) {
         const int s = tid * per + j;
-        if (s < S) local += max((int)dur_f[(size_t)b * S + s], 0);
+        if (s < S) local = fminf(local + clean(dur_f[(size_t)b * S + s]), cap);
     }
-    int incl = local;
+    float incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(kFullMask, incl, o);
-        if (lane >= o) incl += n;
+        const float n = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl = fminf(incl + n, cap);
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    int run = incl - local;
-    for (int w = 0; w < warp; ++w) run += warp_tot[w];
+    float run = 0.0f;
+    for (int w = 0; w < warp; ++w) run = fminf(run + warp_tot[w], cap);
+    run = fminf(run + __shfl_up_sync(kFullMask, incl, 1) * (lane > 0 ? 1.0f : 0.0f), cap);   // exclusive prefix of this thread
     for (int j = 0; j < per; ++j) {
         const int s = tid * per + j;
         if (s < S) {
-            run += max((int)dur_f[(size_t)b * S + s], 0);
+            run = fminf(run + clean(dur_f[(size_t)b * S + s]), cap);
             cum_s[s] = run;  // inclusive: frames [cum[s-1], cum[s]) belong to column s
         }
     }
     __syncthreads();
     const int t_y = t_ys ? min(max(t_ys[b], 0), T) : T;
     for (int y = tid; y < T; y += kScatterThreads) {
+        const float yf = (float)y;
         int lo = 0, hi = t_x;  // first column in [0, t_x) with cum > y, t_x if none
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (cum_s[mid] > y)
+            if (cum_s[mid] > yf)
                 hi = mid;
             else
                 lo = mid + 1;

@@ -1,6 +1,6 @@
-// mas_fused.cu -- neg_cent contraction and MAS in ONE kernel (no-noise alignment path,
-// reference vits2/models.py:1224-1256 with mas_noise_scale None).
+// mas_fused.cu -- neg_cent contraction and MAS in ONE kernel (reference vits2/models.py:1224-1256).
 //
+// No noise (mas_noise_scale None) -- mas_fused_pair_kernel:
 // One CTA per SM.  Every CTA starts in the tcgen05 contraction role (mas_cost_tc.cuh) over the unit list --
 // utterance groups of n_dp, mel-tile-major inside a group -- and publishes every finished 128-row cost tile with
 // a release store to a flag.  After seq_k rounds the first n_dp CTAs leave the contraction and run the forward
@@ -9,10 +9,21 @@
 // planes.  The cost plane round-trips through L2 only; the DP trails the contraction by a few tiles instead of
 // waiting for the whole batch.  Producers never wait on consumers; the launch is cooperative so that all CTAs
 // are co-resident, and a programmatic dependent of the prior-images kernel (fused_launch).
+//
+// VITS2 noise-scaled MAS (models.py:1241-1247) -- mas_fused_noise_kernel:
+// the standard deviation over ALL cost cells has to exist before the first DP row, so the kernel has two phases
+// around a grid barrier: (1) every CTA contracts, the epilogue also accumulates sum / sum of squares; (2) the
+// first n_dp CTAs run the DP exactly as above, the others first add (std * noise) * scale to the L2-resident
+// cost plane tile by tile in mel-tile-major order (raising the same per-tile flags the DP waits on), then
+// zero-fill the path planes.  The DP warps therefore run the plain (no-noise) body; the noise draw is read
+// once from HBM by CTAs that would otherwise idle.
+//
+// The private cost plane has its own row stride (S rounded up to 4 floats), so S and T are arbitrary.
 #include <atomic>
 
 #include "mas_cost_tc.cuh"
 #include "mas_dp.cuh"
+#include "mas_fused.cuh"
 
 namespace mas {
 
@@ -20,26 +31,15 @@ struct FusedParams {
     TcParams tc;
     DpParams dp;
     int n_dp;              // the first n_dp CTAs turn into DP CTAs after their share of the contraction
+    // noise kernel only
+    const float *noise;    // [B][T][S] draw standing in for torch.randn_like(neg_cent)
+    float noise_scale;
+    uint32_t *grid_bar;    // grid barrier counter (cleared with the flags)
 };
 
-template <int C, int R, int W, bool kPair, bool kVK>
-__device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensorMap *tm_z, const CUtensorMap *tm_out,
-                                           unsigned char *smem)
+template <int C, int R, int W, bool kVK>
+__device__ __forceinline__ void fused_dp_ctas(const FusedParams &fp, unsigned char *smem)
 {
-    // every CTA starts in the contraction role; the first n_dp CTAs ("hybrid") leave it after seq_k rounds of
-    // units and become the DP CTAs, the others finish the remaining units (unit_index() in cost_tc_role)
-    if (fp.tc.trace && threadIdx.x == 0) fp.tc.trace[49152 + blockIdx.x] = globaltimer_ns();  // CTA entry
-    if (kPair)
-        cost_tc_role<false, true>(fp.tc, tm_z, tm_out, smem, blockIdx.x >> 1, gridDim.x >> 1);
-    else
-        cost_tc_role<false, false>(fp.tc, tm_z, tm_out, smem, blockIdx.x, gridDim.x);
-    if (fp.tc.trace && threadIdx.x == 0) fp.tc.trace[49152 + 256 + blockIdx.x] = globaltimer_ns();  // contraction role left
-    if ((int)blockIdx.x >= fp.n_dp) {
-        // out of tiles: zero-fill the dense path planes while the DP CTAs are still busy
-        if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem);
-        if (fp.tc.trace && threadIdx.x == 0) fp.tc.trace[49152 + 512 + blockIdx.x] = globaltimer_ns();  // zero-fill done
-        return;
-    }
     // DP CTA j aligns utterances j, j + n_dp, ... on its first dp_threads(W) threads
     if ((int)threadIdx.x >= dp_threads(W, kVK)) return;
     const int j = (int)blockIdx.x;
@@ -49,13 +49,25 @@ __device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensor
         dp_role<C, R, W, true, false, kVK>(fp.dp, smem, b, j, g_base, threadIdx.x, kDpBar);
 }
 
-template <int C, int R, int W, bool kVK>
-__global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_constant__ FusedParams fp,
-                                                                  const __grid_constant__ CUtensorMap tm_z,
-                                                                  const __grid_constant__ CUtensorMap tm_out)
+template <int C, int R, int W, bool kPair, bool kVK>
+__device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensorMap *tm_z, const CUtensorMap *tm_out,
+                                           unsigned char *smem)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
-    fused_body<C, R, W, false, kVK>(fp, &tm_z, &tm_out, smem);
+    // every CTA starts in the contraction role; the first n_dp CTAs ("hybrid") leave it after seq_k rounds of
+    // units and become the DP CTAs, the others finish the remaining units (unit_index() in cost_tc_role)
+    if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + blockIdx.x] = globaltimer_ns();  // CTA entry
+    if (kPair)
+        cost_tc_role<false, true>(fp.tc, tm_z, tm_out, smem, blockIdx.x >> 1, gridDim.x >> 1);
+    else
+        cost_tc_role<false, false>(fp.tc, tm_z, tm_out, smem, blockIdx.x, gridDim.x);
+    if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 256 + blockIdx.x] = globaltimer_ns();  // contraction role left
+    if ((int)blockIdx.x >= fp.n_dp) {
+        // out of tiles: zero-fill the dense path planes while the DP CTAs are still busy
+        if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem);
+        if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 512 + blockIdx.x] = globaltimer_ns();  // zero-fill done
+        return;
+    }
+    fused_dp_ctas<C, R, W, kVK>(fp, smem);
 }
 
 // contraction CTAs in pairs (clusters of 2, n_gemm even); the DP CTAs ignore their cluster
@@ -68,63 +80,229 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     fused_body<C, R, W, true, kVK>(fp, &tm_z, &tm_out, smem);
 }
 
-static int env_int(const char *name, int dflt)
+#ifdef MAS_TRACE
+// single-CTA contraction (cta_group::1), kept for A/B runs in the trace build (MAS_TC_PAIR=0)
+template <int C, int R, int W, bool kVK>
+__global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_constant__ FusedParams fp,
+                                                                  const __grid_constant__ CUtensorMap tm_z,
+                                                                  const __grid_constant__ CUtensorMap tm_out)
 {
-    const char *s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
+    extern __shared__ __align__(128) unsigned char smem[];
+    fused_body<C, R, W, false, kVK>(fp, &tm_z, &tm_out, smem);
 }
+#endif
+
+// ---------------------------------------------------------------------------
+// noise-scaled alignment: contraction + statistics | grid barrier | noise appliers + DP + zero fill
+// ---------------------------------------------------------------------------
+// Adds (sd * noise) * scale to the private cost plane, one 128-row mel tile of one utterance at a time, items
+// in mel-tile-major order strided over the applier CTAs; raises the tile's flag when its rows are in memory.
+// Rounded after every operation like the reference's `std * randn * scale` then `+` (models.py:1242-1247).
+__device__ __forceinline__ void noise_apply_role(const FusedParams &fp, float sd, int rank, int n_appliers)
+{
+    const TcParams &tc = fp.tc;
+    const int T = tc.T, S = tc.S, ld = tc.ld, m_tiles = tc.m_tiles;
+    const int n_items = tc.B * m_tiles;
+    const float scale = fp.noise_scale;
+    const bool vec = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(fp.noise) & 15) == 0);   // (then ld == S)
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int item = rank; item < n_items; item += n_appliers) {
+        const int mt = item / tc.B, b = item - mt * tc.B;
+        const int t_y = fp.dp.t_ys[b];
+        const int r0 = mt * kBM;
+        int r1 = min(r0 + kBM, T);
+        if (t_y >= 1 && t_y <= T) r1 = min(r1, t_y);   // rows past t_y are never read by the DP
+        if (r0 >= r1) continue;
+        float *nc = tc.out + ((size_t)b * T + r0) * ld;
+        const float *nz = fp.noise + ((size_t)b * T + r0) * S;
+        if (vec) {
+            const int n4 = (r1 - r0) * S / 4;
+            float4 *nc4 = reinterpret_cast<float4 *>(nc);
+            const float4 *nz4 = reinterpret_cast<const float4 *>(nz);
+            for (int i = tid; i < n4; i += 4 * nthr) {
+                float4 c[4], n[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u * nthr < n4) {
+                        c[u] = __ldcg(nc4 + i + u * nthr);     // L2 (written by other SMs' TMA stores)
+                        n[u] = __ldcs(nz4 + i + u * nthr);     // streamed once from HBM
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u * nthr < n4) {
+                        c[u].x = __fadd_rn(c[u].x, __fmul_rn(__fmul_rn(sd, n[u].x), scale));
+                        c[u].y = __fadd_rn(c[u].y, __fmul_rn(__fmul_rn(sd, n[u].y), scale));
+                        c[u].z = __fadd_rn(c[u].z, __fmul_rn(__fmul_rn(sd, n[u].z), scale));
+                        c[u].w = __fadd_rn(c[u].w, __fmul_rn(__fmul_rn(sd, n[u].w), scale));
+                        __stcg(nc4 + i + u * nthr, c[u]);
+                    }
+            }
+        } else {
+            const int n = (r1 - r0) * S;
+            for (int i = tid; i < n; i += nthr) {
+                const int r = i / S, x = i - r * S;
+                float *q = nc + (size_t)r * ld + x;
+                *q = __fadd_rn(__ldcg(q), __fmul_rn(__fmul_rn(sd, __ldcs(nz + i)), scale));
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_gpu(fp.dp.flags + (size_t)b * m_tiles + mt, 1u);
+    }
+}
+
+template <int C, int R, int W, bool kVK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+    mas_fused_noise_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CUtensorMap tm_z,
+                           const __grid_constant__ CUtensorMap tm_out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    // phase 1: the whole batch's cost plane + its statistics (no tile flags: nothing may be aligned yet)
+    cost_tc_role<true, true>(fp.tc, &tm_z, &tm_out, smem, blockIdx.x >> 1, gridDim.x >> 1);
+    // grid barrier: every CTA's tiles are in memory and its partial sums are in stats[]
+    fence_proxy_async_all();
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(fp.grid_bar, 1u);
+        while (ld_acquire_gpu(fp.grid_bar) < gridDim.x) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+    if ((int)blockIdx.x >= fp.n_dp) {
+        // unbiased std over ALL cells, padding included (torch.std default, models.py:1243), from fp64 sums
+        const double *st = fp.tc.stats;
+        const double n = (double)fp.tc.B * (double)fp.tc.T * (double)fp.tc.S;
+        const double s0 = __ldcg(st), s1 = __ldcg(st + 1);
+        const double mean = s0 / n;
+        double var = (s1 - s0 * mean) / (n > 1.0 ? n - 1.0 : 1.0);
+        if (var < 0) var = 0;
+        noise_apply_role(fp, (float)sqrt(var), (int)blockIdx.x - fp.n_dp, (int)gridDim.x - fp.n_dp);
+        if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem);
+        return;
+    }
+    fused_dp_ctas<C, R, W, kVK>(fp, smem);
+}
+
+// the private cost plane keeps 16-byte rows whatever S is
+static int padded_ld(int S) { return (S + 3) & ~3; }
 
 bool fused_supported(int B, int D, int T, int S)
 {
-    if (env_int("MAS_NO_FUSED", 0)) return false;
-    // tensor-map stores / vector cost loads need 16-byte rows; the contraction takes S <= 256
-    return cost_tc_supported(B, D, T, S) && (S % 4 == 0) && (T % 4 == 0) && S <= kNMax;
+    if (config().no_fused) return false;
+    // the contraction role of the fused kernel takes one column block (S <= 256)
+    return cost_tc_supported(B, D, T, S) && S <= kNMax;
 }
 
-// tile flags [B][m_tiles], the zero-fill flags [B], the zero-fill queue counter
-size_t fused_flags_bytes(int B, int T) { return align_up(((size_t)B * ((T + kBM - 1) / kBM + 1) + 1) * 4, 256); }
+// noise-scaled alignment in one kernel: the DP CTAs need at least as many noise-applier CTAs next to them
+bool fused_noise_supported(int B, int D, int T, int S)
+{
+    if (!config().noise_fused || !fused_supported(B, D, T, S)) return false;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 2 * B <= (sms & ~1);
+}
 
+// tile flags [B][m_tiles], the zero-fill flags [B], the zero-fill queue counter, the grid barrier counter
+size_t fused_flags_bytes(int B, int T) { return align_up(((size_t)B * ((T + kBM - 1) / kBM + 1) + 2) * 4, 256); }
+// bytes of the private cost plane inside the fused workspace
+size_t fused_plane_bytes(int B, int T, int S) { return align_up((size_t)B * T * padded_ld(S) * 4, 256); }
+
+// Launches the prior preparation and one fused kernel.  Returns MAS_OK, an error, or kFusedFallback when the
+// cooperative launch is not possible in this context (MPS / MIG / green-context limits, no tensor maps): the
+// caller then runs contraction and DP as separate launches.
 int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const int32_t *t_ys, const int32_t *t_xs,
-                 float *neg_cent, bool skip_dead_tiles, void *path_out, int path_dtype, int32_t *dur_out,
-                 int32_t *idx_out, int32_t *status_out, void *cost_ws, size_t cost_ws_bytes, void *dp_ws,
+                 const float *noise, float noise_scale, double *stats, float *plane, void *path_out, int path_dtype,
+                 int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *cost_ws, size_t cost_ws_bytes, void *dp_ws,
                  size_t dp_ws_bytes, uint32_t *flags, int B, int D, int T, int S, cudaStream_t stream)
 {
     int dev = 0, sms = 148;
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const Config &cf = config();
     const int m_tiles = (T + kBM - 1) / kBM;
+    const int ld = padded_ld(S);
+    const int n_flags = B * (m_tiles + 1) + 2;
     TcPlan tc;
-    int rc = cost_tc_prepare(tc, z_p, m_p, logs_p, neg_cent, nullptr, skip_dead_tiles ? t_ys : nullptr, cost_ws,
-                             cost_ws_bytes, B, D, T, S, flags, B * (m_tiles + 1) + 1, stream);
+    // mel tiles wholly past t_y are skipped (the plane is private scratch) unless the noise statistics need them
+    int rc = cost_tc_prepare(tc, z_p, m_p, logs_p, plane, noise ? stats : nullptr, noise ? nullptr : t_ys, cost_ws,
+                             cost_ws_bytes, B, D, T, S, flags, n_flags, stream, ld);
     if (rc) return rc;
-    if (!tc.p.z_tma || !tc.p.out_tma) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (cf.stage == 1) return MAS_OK;   // prior preparation only (bench.py times it alone)
+    if (!tc.p.out_tma) return kFusedFallback;
     DpPlan dp;
-    rc = dp_prepare(dp, neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T,
-                    S, nullptr, 0, 0);
+    rc = dp_prepare(dp, plane, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T,
+                    S, nullptr, 0, 0, false, ld);
     if (rc) return rc;
-    FusedParams fp;
+    FusedParams fp{};
     fp.tc = tc.p;
     fp.dp = dp.p;
-    // DP CTAs (MAS_FUSED_DP_CTAS overrides): one per utterance; when the batch is larger than the GPU, nearly
-    // every CTA becomes a DP CTA after the contraction and aligns several utterances in turn (the standalone
-    // MAS kernel reaches the HBM roofline that way: the DP wants every SM's memory pipe)
-    const bool pair = cost_tc_pair_enabled();
-    const int grid = pair ? (sms & ~1) : sms;
+    fp.noise = noise;
+    fp.noise_scale = noise_scale;
+    const bool pair = noise ? true : cost_tc_pair_enabled();
     const int per = pair ? 2 : 1;
+
+#ifdef MAS_TRACE
+#define MAS_FUSED_KERNEL(CC, WW, VK)                                                                       \
+    (noise  ? (const void *)mas_fused_noise_kernel<CC, 32, WW, VK>                                         \
+     : pair ? (const void *)mas_fused_pair_kernel<CC, 32, WW, VK>                                          \
+            : (const void *)mas_fused_kernel<CC, 32, WW, VK>)
+#else
+#define MAS_FUSED_KERNEL(CC, WW, VK) \
+    (noise ? (const void *)mas_fused_noise_kernel<CC, 32, WW, VK> : (const void *)mas_fused_pair_kernel<CC, 32, WW, VK>)
+#endif
+    // S <= 256 (one column block): C = ceil(S / 64) columns per thread with 2 DP warps, or 2 columns with 4
+    // (value / origin warp split unless MAS_DP_VK=0)
+    const void *kernel = nullptr;
+#define MAS_FUSED_CASE(CC, WW, VK) \
+    if (dp.C == CC && dp.p.R == 32 && dp.p.W == WW && (dp.p.vk != 0) == VK) kernel = MAS_FUSED_KERNEL(CC, WW, VK);
+    MAS_FUSED_CASE(1, 2, true)
+    MAS_FUSED_CASE(2, 2, true)
+    MAS_FUSED_CASE(3, 2, true)
+    MAS_FUSED_CASE(4, 2, true)
+    MAS_FUSED_CASE(2, 4, true)
+    MAS_FUSED_CASE(1, 2, false)
+    MAS_FUSED_CASE(2, 2, false)
+    MAS_FUSED_CASE(3, 2, false)
+    MAS_FUSED_CASE(4, 2, false)
+#undef MAS_FUSED_CASE
+#undef MAS_FUSED_KERNEL
+    if (!kernel) return kFusedFallback;
+
+    size_t smem = dp.smem_bytes;
+    if (smem < kTcSmem) smem = kTcSmem;
+    if (smem < kZeroFillBuf) smem = kZeroFillBuf;
+    // all CTAs must be co-resident (the DP CTAs spin on flags the others raise): check what this context can
+    // actually hold, one CTA per SM at most
+    MAS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTcThreads, smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        return kFusedFallback;
+    }
+    const int grid = pair ? (sms & ~1) : sms;
     const int units = B * (pair ? (m_tiles + 1) / 2 : m_tiles);
-    // Unit schedule: all CTAs take seq_k rounds of units, then the DP CTAs leave.  A small cost model (unit
-    // ~7 us, DP ~40 ns per mel row + 8 us per utterance) picks seq_k and, for batches larger than 64, between
-    // 64 DP CTAs and nearly all of them: the contraction must not end long after the DP could, and the DP
-    // must not start long before its tiles exist.
+
+    // Unit schedule: all CTAs take seq_k rounds of units, then the DP CTAs leave.  A small cost model picks
+    // seq_k and, for batches larger than 64, between 64 DP CTAs and nearly all of them: the contraction must
+    // not end long after the DP could, and the DP must not start long before its tiles exist.
+    //   unit: the bytes one SM moves per unit through its TMA path (~60 GB/s) or the MMA time, whichever is longer
+    //   DP:   ~ (16 + 10 C) cycles per mel row with the value / origin split, + 8 us per utterance (backtrack, outputs)
+    const int n_kb = tc.p.n_kb, n_cols = (S + 15) & ~15;
+    const double unit_bytes = (double)kBM * D * 4 + (double)n_kb * 2 * (n_cols / per) * kRowBytes + (double)kBM * n_cols * 4;
+    const double t_mma = 4.7 * (n_cols / 256.0) * (D / 192.0);
+    const double t_u = unit_bytes / 60e3 > t_mma ? unit_bytes / 60e3 : t_mma;
+    const double t_row = 0.040 * (16.0 + 10.0 * dp.C) / 56.0;
     auto model = [&](int n_dp_try, int &k_out) {
         const int P = grid / per, P_pure = (grid - n_dp_try) / per;
         const int utts = (B + n_dp_try - 1) / n_dp_try;
         double best = 1e30;
         for (int k = 0; k <= 64; ++k) {
             const int rest = units - k * P > 0 ? units - k * P : 0;
-            const double t_u = 7.0;
             const double gemm_end = (k + (rest + P_pure - 1) / P_pure) * t_u;
-            const double dp_end = k * t_u + utts * (T * 0.040 + 8.0);
+            const double dp_end = k * t_u + utts * (T * t_row + 8.0);
             const double t = (gemm_end + 8.0 > dp_end) ? gemm_end + 8.0 : dp_end;
             if (t < best - 1e-9) best = t, k_out = k;
             if (rest == 0) break;
@@ -137,8 +315,11 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
         if (n > grid - 8) n = (grid - 8) & ~1;
         return n;
     };
-    int n_dp = env_int("MAS_FUSED_DP_CTAS", 0), best_k = 0;
-    if (n_dp > 0) {
+    int n_dp = cf.fused_dp_ctas, best_k = 0;
+    if (noise) {
+        n_dp = legal(B);             // fused_noise_supported(): at least as many appliers as DP CTAs
+        best_k = 1 << 28;            // nobody leaves the contraction before the barrier
+    } else if (n_dp > 0) {
         n_dp = legal(n_dp);
         model(n_dp, best_k);
     } else {
@@ -148,24 +329,22 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
         n_dp = (t_b < t_a) ? n_b : n_a;
         best_k = (t_b < t_a) ? k_b : k_a;
     }
-    if (n_dp < 1) return MAS_ERR_UNSUPPORTED_SHAPE;
+    if (n_dp < 1) return kFusedFallback;
     fp.n_dp = n_dp;
     const int utts_per_cta = (B + n_dp - 1) / n_dp;
-    fp.tc.seq_k = env_int("MAS_FUSED_ROUNDS", -1) >= 0 ? env_int("MAS_FUSED_ROUNDS", -1) : best_k;
-    fp.tc.seq_pure0 = n_dp / per;
-    fp.tc.wave = fp.n_dp;
-    fp.tc.flags = flags;
+    fp.tc.seq_k = (!noise && cf.fused_rounds >= 0) ? cf.fused_rounds : best_k;
+    fp.tc.seq_pure0 = noise ? 0 : n_dp / per;
+    fp.tc.wave = noise ? B : fp.n_dp;
+    fp.tc.flags = noise ? nullptr : flags;    // noise: the appliers raise the flags, not the epilogue
     fp.dp.flags = flags;
     fp.tc.trace = trace_buffer();
     fp.dp.trace = fp.tc.trace;
     fp.dp.flag_tiles = m_tiles;
     // the contraction-only CTAs zero-fill the path planes when there are enough of them to do it in time
-    const bool offload = env_int("MAS_FUSED_ZERO_OFFLOAD", 1) && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1;
+    const bool offload = path_out && cf.fused_zero_offload && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1;
     fp.dp.zero_flags = offload ? flags + (size_t)B * m_tiles : nullptr;
     fp.dp.zero_queue = flags + (size_t)B * (m_tiles + 1);
-    size_t smem = dp.smem_bytes;
-    if (smem < kTcSmem) smem = kTcSmem;
-    if (smem < kZeroFillBuf) smem = kZeroFillBuf;
+    fp.grid_bar = flags + (size_t)B * (m_tiles + 1) + 1;
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -180,49 +359,19 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     static std::atomic<int> pdl_state{-1};  // -1 untested, 0 refused, 1 works (calls may come from several threads)
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cap);
-    bool use_pdl = env_int("MAS_FUSED_PDL", 1) && (pdl_state == 1 || (pdl_state < 0 && cap == cudaStreamCaptureStatusNone));
+    bool use_pdl = cf.fused_pdl && (pdl_state == 1 || (pdl_state < 0 && cap == cudaStreamCaptureStatusNone));
     cudaLaunchAttribute attr[2];
-    int n_attr = 0;
-    if (env_int("MAS_FUSED_COOP", 1)) {
-        attr[n_attr].id = cudaLaunchAttributeCooperative;
-        attr[n_attr].val.cooperative = 1;
-        ++n_attr;
-    }
-    if (use_pdl) {
-        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
-        ++n_attr;
-    }
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = n_attr;
     fp.tc.pdl = 1;  // (the wait is a no-op under a plain launch)
+    void *args[3] = {&fp, &tc.tm_z, &tc.tm_out};
     cudaError_t e = cudaErrorInvalidValue;
-#define MAS_FUSED_CASE(CC, WW, VK)                                                                               \
-    if (dp.C == CC && dp.p.R == 32 && dp.p.W == WW && (dp.p.vk != 0) == VK) {                                    \
-        static thread_local int cfg_dev = -1;                                                                    \
-        if (dev != cfg_dev) {                                                                                    \
-            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_kernel<CC, 32, WW, VK>,                                  \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));        \
-            MAS_CUDA_TRY(cudaFuncSetAttribute(mas_fused_pair_kernel<CC, 32, WW, VK>,                             \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));        \
-            cfg_dev = dev;                                                                                       \
-        }                                                                                                        \
-        e = pair ? cudaLaunchKernelEx(&cfg, mas_fused_pair_kernel<CC, 32, WW, VK>, fp, tc.tm_z, tc.tm_out)       \
-                 : cudaLaunchKernelEx(&cfg, mas_fused_kernel<CC, 32, WW, VK>, fp, tc.tm_z, tc.tm_out);           \
-    }
-    // S <= 256 (the contraction's limit): C = ceil(S / 64) columns per thread with 2 DP warps (value /
-    // bookkeeping split by default), or ceil(S / 128) with 4 (MAS_DP_WARPS=4)
     for (int attempt = 0; attempt < 2; ++attempt) {
-    MAS_FUSED_CASE(1, 2, true)
-    else MAS_FUSED_CASE(2, 2, true)
-    else MAS_FUSED_CASE(3, 2, true)
-    else MAS_FUSED_CASE(4, 2, true)
-    else MAS_FUSED_CASE(1, 2, false)
-    else MAS_FUSED_CASE(2, 2, false)
-    else MAS_FUSED_CASE(3, 2, false)
-    else MAS_FUSED_CASE(4, 2, false)
-    else MAS_FUSED_CASE(2, 4, false)
-    else return MAS_ERR_UNSUPPORTED_SHAPE;
+        cfg.numAttrs = use_pdl ? 2 : 1;
+        e = cudaLaunchKernelExC(&cfg, kernel, args);
         if (!use_pdl) break;
         if (e == cudaSuccess) {
             pdl_state = 1;
@@ -232,9 +381,12 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
         (void)cudaGetLastError();
         pdl_state = 0;
         use_pdl = false;
-        cfg.numAttrs = n_attr - 1;  // the programmatic attribute is the last one
     }
-#undef MAS_FUSED_CASE
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+        // this context cannot hold the whole grid (MPS thread percentage, MIG slice, green context): not an error
+        (void)cudaGetLastError();
+        return kFusedFallback;
+    }
     note_launch();
     if (e != cudaSuccess) return note_cuda_error(e, "cudaLaunchKernelEx(mas_fused_kernel)");
     return MAS_OK;

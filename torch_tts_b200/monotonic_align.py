@@ -31,7 +31,8 @@ def lengths_from_mask(mask: torch.Tensor):
 def maximum_path_compact(neg_cent: torch.Tensor, t_ys: torch.Tensor, t_xs: torch.Tensor, *,
                          want_path: bool = True, path_dtype=None):
     """MAS from explicit lengths.  Returns (path | None, durations int32 [B,S],
-    idx int32 [B,T] (-1 past t_y), status int32 [B])."""
+    idx int32 [B,T] (-1 past t_y), status int32 [B]).  want_path=False: the dense plane is neither
+    allocated nor written (the kernel then only reads neg_cent and writes the compact outputs)."""
     _lib.require_cuda(neg_cent, "neg_cent")
     if neg_cent.dim() != 3:
         raise _lib.MasError(f"neg_cent must be [b, t_t, t_s], got {tuple(neg_cent.shape)}")
@@ -49,7 +50,7 @@ def maximum_path_compact(neg_cent: torch.Tensor, t_ys: torch.Tensor, t_xs: torch
     kdtype = out_dtype if out_dtype in _lib.PATH_DTYPES else torch.float32
     L = _lib.lib()
     with torch.cuda.device(device):
-        path = torch.empty((B, T, S), dtype=kdtype, device=device)
+        path = torch.empty((B, T, S), dtype=kdtype, device=device) if want_path else None
         dur = torch.empty((B, S), dtype=torch.int32, device=device)
         idx = torch.empty((B, T), dtype=torch.int32, device=device)
         status = torch.empty((B,), dtype=torch.int32, device=device)
@@ -61,9 +62,9 @@ def maximum_path_compact(neg_cent: torch.Tensor, t_ys: torch.Tensor, t_xs: torch
                                     _lib.PATH_DTYPES[kdtype], _lib.ptr(dur), _lib.ptr(idx), _lib.ptr(status),
                                     _lib.ptr(ws), ws.numel(), B, T, S, _lib.stream_ptr(device))
     _lib.check(rc, "mas_maximum_path_f32")
-    if kdtype != out_dtype:
+    if want_path and kdtype != out_dtype:
         path = path.to(out_dtype)
-    return (path if want_path else None), dur, idx, status
+    return path, dur, idx, status
 
 
 def maximum_path(neg_cent: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:

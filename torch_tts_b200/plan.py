@@ -11,11 +11,17 @@ from . import _lib
 
 
 class AlignPlan:
-    def __init__(self, B: int, D: int, T: int, S: int, device, dtype=torch.float32, with_noise: bool = False):
+    def __init__(self, B: int, D: int, T: int, S: int, device, dtype=torch.float32, with_noise: bool = False,
+                 want_path: bool = True):
+        """want_path=False: compact outputs only (self.idx / self.dur / self.status); the dense path plane is
+        neither allocated nor written -- `expand_path(plan.idx, S)` rebuilds it on demand."""
         self.B, self.D, self.T, self.S = B, D, T, S
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = dtype
         self.with_noise = with_noise
+        self.want_path = want_path
         if dtype not in _lib.PATH_DTYPES:
             raise _lib.MasError(f"unsupported path dtype {dtype}")
         L = _lib.lib()
@@ -24,7 +30,7 @@ class AlignPlan:
             raise _lib.MasError(f"unsupported shape B={B} D={D} T={T} S={S}")
         with torch.cuda.device(self.device):
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self.path = torch.empty((B, T, S), dtype=dtype, device=self.device)
+            self.path = torch.empty((B, T, S), dtype=dtype, device=self.device) if want_path else None
             self.dur = torch.empty((B, S), dtype=torch.int32, device=self.device)
             self.idx = torch.empty((B, T), dtype=torch.int32, device=self.device)
             self.status = torch.empty((B,), dtype=torch.int32, device=self.device)
@@ -32,15 +38,33 @@ class AlignPlan:
         self._graphs = {}
 
     def run(self, z_p, m_p, logs_p, t_ys, t_xs, noise=None, noise_scale: float = 0.0):
-        """Stream-ordered on the current stream; results land in self.path/dur/idx/status."""
-        rc = self._L.mas_fused_align_f32(
-            z_p.data_ptr(), m_p.data_ptr(), logs_p.data_ptr(), t_ys.data_ptr(), t_xs.data_ptr(),
-            None if noise is None else noise.data_ptr(), float(noise_scale), self.path.data_ptr(),
-            _lib.PATH_DTYPES[self.dtype], self.dur.data_ptr(), self.idx.data_ptr(), self.status.data_ptr(), None,
-            self.ws.data_ptr(), self.ws.numel(), self.B, self.D, self.T, self.S,
-            torch.cuda.current_stream(self.device).cuda_stream)
+        """Stream-ordered on the current stream of the plan's device; results land in self.path/dur/idx/status.
+        Inputs must be fp32, contiguous, on the plan's device, of the plan's shapes (under autocast: upcast first,
+        as `align()` does) -- checked here, the kernels read raw pointers."""
+        B, D, T, S = self.B, self.D, self.T, self.S
+        self._check("z_p", z_p, (B, D, T), torch.float32)
+        self._check("m_p", m_p, (B, D, S), torch.float32)
+        self._check("logs_p", logs_p, (B, D, S), torch.float32)
+        self._check("t_ys", t_ys, (B,), torch.int32)
+        self._check("t_xs", t_xs, (B,), torch.int32)
+        if noise is not None:
+            self._check("noise", noise, (B, T, S), torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self._L.mas_fused_align_f32(
+                z_p.data_ptr(), m_p.data_ptr(), logs_p.data_ptr(), t_ys.data_ptr(), t_xs.data_ptr(),
+                None if noise is None else noise.data_ptr(), float(noise_scale),
+                None if self.path is None else self.path.data_ptr(),
+                _lib.PATH_DTYPES[self.dtype], self.dur.data_ptr(), self.idx.data_ptr(), self.status.data_ptr(), None,
+                self.ws.data_ptr(), self.ws.numel(), B, D, T, S,
+                torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             _lib.check(rc, "mas_fused_align_f32")
+
+    def _check(self, name, t, shape, dtype):
+        if t.device != self.device or t.dtype != dtype or tuple(t.shape) != shape or not t.is_contiguous():
+            raise _lib.MasError(f"AlignPlan.run: {name} must be a contiguous {dtype} tensor of shape {shape} on "
+                                f"{self.device}, got {t.dtype} {tuple(t.shape)} on {t.device}"
+                                f"{'' if t.is_contiguous() else ' (not contiguous)'}")
 
     def capture(self, key, z_p, m_p, logs_p, t_ys, t_xs, noise=None, noise_scale: float = 0.0):
         """Capture one step on these (static) input buffers into a CUDA graph; replay(key) launches it."""

@@ -19,24 +19,34 @@ def shard_bounds(batch: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_compact(idx: torch.Tensor, dur: torch.Tensor, batch: int, group=None):
-    """All-gather per-rank compact results into global [batch, T] / [batch, S].
-    Ragged shards are padded to the largest shard for the collective."""
+def gather_compact(idx: torch.Tensor, dur: torch.Tensor, batch=None, group=None):
+    """All-gather per-rank compact results into global [batch, T_max] / [batch, S_max].
+
+    Ranks may hold different numbers of utterances AND different padded sizes: under DDP every rank's batch is
+    padded by TextAudioCollate to its own longest text / spectrogram (data_utils.py:168-177), so T and S differ
+    from rank to rank.  The ranks first agree on (shard size, T, S) maxima with one small all-gather, then every
+    rank pads to them (idx with -1 = "no frame", durations with 0) for the one data collective.
+    `batch`, when given, is checked against the gathered total."""
     world = dist.get_world_size(group)
-    per = (batch + world - 1) // world
-    T, S = idx.shape[1], dur.shape[1]
-    packed = torch.full((per, T + S), -1, dtype=torch.int32, device=idx.device)
-    n = idx.shape[0]
+    n, T = idx.shape
+    S = dur.shape[1]
+    mine = torch.tensor([n, T, S], dtype=torch.int64, device=idx.device)
+    sizes = torch.empty((world * 3,), dtype=torch.int64, device=idx.device)
+    dist.all_gather_into_tensor(sizes, mine, group=group)
+    sizes = sizes.view(world, 3).cpu()
+    per, Tg, Sg = (int(v) for v in sizes.max(0).values)
+    packed = torch.empty((per, Tg + Sg), dtype=torch.int32, device=idx.device)
+    packed[:, :Tg] = -1
+    packed[:, Tg:] = 0
     packed[:n, :T] = idx
-    packed[:n, T:] = dur
-    out = torch.empty((world * per, T + S), dtype=torch.int32, device=idx.device)
+    packed[:n, Tg:Tg + S] = dur
+    out = torch.empty((world * per, Tg + Sg), dtype=torch.int32, device=idx.device)
     dist.all_gather_into_tensor(out, packed, group=group)
-    rows = []
-    for r in range(world):
-        lo, hi = shard_bounds(batch, r, world)
-        rows.append(out[r * per: r * per + (hi - lo)])
+    rows = [out[r * per: r * per + int(sizes[r, 0])] for r in range(world)]
     full = torch.cat(rows, 0)
-    return full[:, :T].contiguous(), full[:, T:].contiguous()
+    if batch is not None and full.shape[0] != batch:
+        raise _lib.MasError(f"gather_compact: ranks hold {full.shape[0]} utterances in total, caller expected {batch}")
+    return full[:, :Tg].contiguous(), full[:, Tg:].contiguous()
 
 
 def expand_path(idx: torch.Tensor, S: int, dtype=torch.float32) -> torch.Tensor:
@@ -64,7 +74,5 @@ def align_sharded(z_p, m_p, logs_p, x_mask, y_mask, mas_noise_scale=None, noise=
                                         return_compact=True)
     if not gather:
         return attn, w
-    world = dist.get_world_size(group)
-    batch = global_batch if global_batch is not None else idx.shape[0] * world
-    g_idx, g_dur = gather_compact(idx, dur, batch, group)
+    g_idx, g_dur = gather_compact(idx, dur, global_batch, group)
     return attn, w, g_idx, g_dur
