@@ -761,6 +761,16 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     tc_fence_before();
     bar_sync(1, kTcThreads);
     if (kPair) cluster_sync_all();  // nothing of the peer is in flight towards this CTA any more
+    // The fused kernels reuse this shared memory for the DP role.  Barrier words must be invalidated before they
+    // become plain data: without it the DP role's zero page (which overlays them) kept stale barrier words in the
+    // bulk-store engine's view and the path planes came out with 16-byte holes (config 3, ragged B = 128).
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) mbar_inval(&full[i]), mbar_inval(&empty[i]), mbar_inval(&bfull[i]);
+        for (int i = 0; i < kZStages; ++i) mbar_inval(&zfull[i]), mbar_inval(&zempty[i]);
+        for (int i = 0; i < 2; ++i)
+            mbar_inval(&acc_full[i]), mbar_inval(&acc_empty[i]), mbar_inval(&bias_full[i]), mbar_inval(&bias_empty[i]);
+    }
+    bar_sync(1, kTcThreads);
     if (warp == 2) {
         if (kPair)
             tmem_dealloc2(tmem_base, 512);

@@ -36,6 +36,7 @@ class AlignPlan:
             self.status = torch.empty((B,), dtype=torch.int32, device=self.device)
         self._L = L
         self._graphs = {}
+        self._inputs = {}
 
     def run(self, z_p, m_p, logs_p, t_ys, t_xs, noise=None, noise_scale: float = 0.0):
         """Stream-ordered on the current stream of the plan's device; results land in self.path/dur/idx/status.
@@ -74,6 +75,9 @@ class AlignPlan:
         with torch.cuda.graph(g):
             self.run(z_p, m_p, logs_p, t_ys, t_xs, noise, noise_scale)
         self._graphs[key] = g
+        # the graph reads these buffers on every replay: keep them alive (a caller passing temporaries, e.g.
+        # `t_y.to(device)`, would otherwise replay on freed memory)
+        self._inputs[key] = (z_p, m_p, logs_p, t_ys, t_xs, noise)
         return g
 
     def replay(self, key):
