@@ -115,28 +115,25 @@ def test_arbitrary_shapes_take_the_one_kernel_path(cuda_device, B, S, T, scale):
 # --------------------------------------------------------------------------
 # noise-scaled alignment in one launch
 # --------------------------------------------------------------------------
-@pytest.mark.parametrize("B,S,T,ragged", [(64, 256, 1024, False), (74, 64, 256, True), (1, 256, 1024, False), (20, 200, 800, True)])
+@pytest.mark.parametrize("B,S,T,ragged", [(64, 256, 1024, False), (74, 64, 256, True), (1, 256, 1024, False),
+                                          (20, 200, 800, True), (80, 64, 256, True), (200, 96, 300, True),
+                                          (9, 187, 743, True), (5, 33, 130, True)])
 def test_noise_branch_is_two_launches_and_matches_the_separate_kernels(cuda_device, mas_env, B, S, T, ragged):
-    """B <= 74: prior preparation + one kernel (contraction + statistics | grid barrier | noise appliers + DP).
-    Bit-identical to the three-launch route (MAS_NOISE_FUSED=0), which adds the noise inside the DP."""
+    """Any batch size: prior preparation + ONE kernel (contraction + statistics | grid barrier | DP whose helper
+    warps add the noise to the cost tiles in shared memory).  Bit-identical to the three-launch route
+    (MAS_NOISE_FUSED=0), which adds the noise inside the DP loop (or, for rows that are not 16-byte, in a separate
+    pass over the plane); B > 148 puts several utterances on one DP CTA; S, T need not be multiples of 4."""
     t_x, t_y, host, dev = _inputs(B, S, T, seed=11, ragged=ragged, dev=cuda_device)
     noise = torch.randn((B, T, S), generator=torch.Generator().manual_seed(3)).to(cuda_device)
     (a, w, (idx, dur, status)), n = _launches(lambda: tts.align(*dev, 0.01, noise, return_compact=True))
-    assert n == 2, n
+    # (the DP CTAs stream the draw with 16-byte bulk copies: rows that are not a multiple of 16 bytes take the
+    # separate launches)
+    assert (n == 2) if S % 4 == 0 else (n >= 3), n
     assert (status == 0).all() and torch.equal(dur.sum(1).cpu(), t_y)
     mas_env(MAS_NOISE_FUSED=0)
     (a3, w3, (idx3, dur3, status3)), n3 = _launches(lambda: tts.align(*dev, 0.01, noise, return_compact=True))
-    assert n3 == 3, n3
+    assert n3 >= 3, n3
     assert torch.equal(idx, idx3) and torch.equal(dur, dur3) and torch.equal(a, a3)
-
-
-def test_noise_branch_large_batch_keeps_separate_launches(cuda_device):
-    B, S, T = 80, 64, 256
-    t_x, t_y, host, dev = _inputs(B, S, T, seed=12, dev=cuda_device)
-    noise = torch.randn((B, T, S), device=cuda_device)
-    (a, w, (idx, dur, status)), n = _launches(lambda: tts.align(*dev, 0.01, noise, return_compact=True))
-    assert n == 3, n
-    assert (status == 0).all() and torch.equal(dur.sum(1).cpu(), t_y)
 
 
 def test_noise_graph_replay_is_repeatable(cuda_device):

@@ -62,3 +62,8 @@ for name, off, labels in [("DP warp 0", 0, ["tile wait", "compute", "bits/hop", 
     print(f"{name}: {tot:.0f} cycles in the step loop ({tot / n_steps:.0f} per step)")
     for j, lab in enumerate(labels):
         print(f"   {lab:16s} {tr[:, off + j].mean():9.0f} ({tr[:, off + j].mean() / tot:5.1%})")
+for c in (0, 2, 70, 146):
+    u = buf[16384 + c * 64:16384 + c * 64 + 64].astype(np.int64).reshape(4, 16)
+    for role, nm in ((0, "MMA"), (1, "epilogue")):
+        v = u[role][u[role] > 0]
+        print(f"cta {c} {nm} unit begin/end:", np.round(rel(v), 1).tolist())

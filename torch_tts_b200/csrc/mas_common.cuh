@@ -128,6 +128,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// prefetch the 128-byte line holding `p` into L2
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 1-D bulk copy shared -> global (SASS: UBLKCP); completion tracked by bulk groups.
 __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
 {

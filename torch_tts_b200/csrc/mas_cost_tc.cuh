@@ -218,6 +218,30 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
     lo = pack_bf16x2(x0 - h0, x1 - h1);
 }
 
+// packed fp32 pairs (Blackwell f32x2 arithmetic: one instruction per two cells, each half rounded like the scalar op)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 struct TcParams {
     const float *z_p;
     const unsigned char *images;   // [B][n_blocks][n_kb][2 parts][kBPart]
@@ -557,6 +581,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             const int c_base = nb * kNMax, ncols = block_cols(nb), s_left = p.S - c_base;
             float *orow = p.out + ((size_t)b * p.T + t) * p.ld + c_base;
             const uint32_t taddr = tmem_base + a * kNMax + ((uint32_t)(wq * 32) << 16);
+            uint64_t us0 = 0ull, us1 = 0ull, uq0 = 0ull, uq1 = 0ull;   // packed fp32 {sum, sum} / {sum sq, sum sq} of the unit
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c0, r);
@@ -569,37 +594,31 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     v[j + 2] = __uint_as_float(r[j + 2]) + b4.z, v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
                 }
                 if (kStats) {
-                    // noise statistics: sum and sum of squares of every real cell.  Per 32-column block the
-                    // thread works in fp32 around a pivot (its first value of the block), where the squares
-                    // are small and nothing cancels, and folds the block into the fp64 totals with exact
-                    // algebra: sum v = sum d + n c, sum v^2 = sum d^2 + 2 c sum d + n c^2.  (Three fp64
-                    // operations per cell here made the epilogue the slowest role: +22 us per config-2 batch.)
+                    // noise statistics: sum and sum of squares of every real cell (models.py:1243 takes the std over
+                    // ALL cells, padding included).  fp32 per thread and unit (<= 256 cells of one mel row: the
+                    // rounding errors are unbiased and average out over the 10^7 row sums; measured against the
+                    // fp64 statistics in tests/test_gpu_round2.py), packed two cells per instruction, folded into
+                    // fp64 once per unit.  (A per-block fp32 pivot with fp64 folds cost 3 + operations per cell and
+                    // made the epilogue the slowest role: 10 us per unit against 6.5 us of MMA time.)
                     if (t < p.T && s_left > c0) {
-                        const float c = v[0];
-                        float sd = 0.0f, sdd = 0.0f, sd1 = 0.0f, sdd1 = 0.0f;
-                        int n = 32;
                         if (s_left - c0 >= 32) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) {  // two chains
-                                const float d0 = v[j] - c, d1 = v[j + 1] - c;
-                                sd += d0, sd1 += d1;
-                                sdd = fmaf(d0, d0, sdd), sdd1 = fmaf(d1, d1, sdd1);
+                            for (int j = 0; j < 32; j += 4) {
+                                const uint64_t a = f2_pack(v[j], v[j + 1]), b2 = f2_pack(v[j + 2], v[j + 3]);
+                                us0 = f2_add(us0, a), us1 = f2_add(us1, b2);
+                                uq0 = f2_fma(a, a, uq0), uq1 = f2_fma(b2, b2, uq1);
                             }
-                            sd += sd1, sdd += sdd1;
                         } else {
-                            n = 0;
+                            float ts = 0.f, tq = 0.f;
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (c0 + j < s_left) {
-                                    const float dv = v[j] - c;
-                                    sd += dv;
-                                    sdd = fmaf(dv, dv, sdd);
-                                    ++n;
+                                    ts += v[j];
+                                    tq = fmaf(v[j], v[j], tq);
                                 }
+                            us0 = f2_add(us0, f2_pack(ts, 0.f));
+                            uq0 = f2_add(uq0, f2_pack(tq, 0.f));
                         }
-                        const double cd = (double)c, nd = (double)n, sdd64 = (double)sdd, sd64 = (double)sd;
-                        ssum += sd64 + nd * cd;
-                        ssq += sdd64 + 2.0 * cd * sd64 + nd * cd * cd;
                     }
                 }
                 if MAS_DBG(p, 2) continue;
@@ -628,6 +647,12 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     for (int j = 0; j < 32; ++j)
                         if (c0 + j < s_left) orow[c0 + j] = v[j];
                 }
+            }
+            if (kStats) {
+                float a0, a1, a2, a3, q0, q1, q2, q3;
+                f2_unpack(us0, a0, a1), f2_unpack(us1, a2, a3), f2_unpack(uq0, q0, q1), f2_unpack(uq1, q2, q3);
+                ssum += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+                ssq += ((double)q0 + (double)q1) + ((double)q2 + (double)q3);
             }
             tc_fence_before();
             if (tid == 128) tr_mark(1, nt, 1);

@@ -8,7 +8,7 @@ namespace mas {
 // host: shared-memory plan
 // ---------------------------------------------------------------------------
 bool dp_plan_try(DpPlan &pl, int T, int S, int ld, int W, int C, int R, int stages, bool bits_smem, bool hop_smem,
-                 size_t budget, bool with_noise, bool vk)
+                 size_t budget, bool with_noise, bool vk, int help = 0)
 {
     const int S_pad = W * 32 * C;
     const int n_blk = (T + kCheck - 1) / kCheck;  // 32-row blocks of decision words
@@ -31,6 +31,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int ld, int W, int C, int R, int stag
     off = align_up(off, 128);
     p.off_stage = (uint32_t)off;
     off += (size_t)stages * p.stage_bytes;
+    p.help = help;
     p.off_bnd_v = (uint32_t)off;
     off += (size_t)(W + 1) * 2 * R * 4;
     p.off_bnd_o = (uint32_t)off;
@@ -66,7 +67,7 @@ int dp_team_warps(int S)
 }
 
 bool dp_make_plan(DpPlan &pl, int B, int T, int S, int ld, int stages_hint, int R_hint, size_t budget, bool with_noise,
-                  bool vk)
+                  bool vk, int help = 0)
 {
     const int W = dp_team_warps(S);
     const int C = (S + W * 32 - 1) / (W * 32);
@@ -78,7 +79,10 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int ld, int stages_hint, int 
     bool ok = false;
     if (vk) {
         // warp split: everything on chip, one tile of prefetch distance at least, or not at all
-        for (int st = 5; st >= W + 1 && !ok; --st) ok = dp_plan_try(pl, T, S, ld, W, C, R0, st, true, true, budget, false, true);
+        // (with helper warps one more chunk is in use at any time: the one being noised)
+        const int min_st = W + 1 + (help > 0 ? 1 : 0);
+        for (int st = 5; st >= min_st && !ok; --st)
+            ok = dp_plan_try(pl, T, S, ld, W, C, R0, st, true, true, budget, false, true, help);
         if (!ok) return false;
         pl.ws_bits_bytes = pl.ws_hop_bytes = 0;
         return true;
@@ -248,7 +252,7 @@ static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
                size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget,
-               bool with_noise, int ld)
+               bool with_noise, int ld, int help)
 {
     pl = DpPlan{};
     if (ld <= 0) ld = S;   // cost rows packed like the caller's [B,T,S] tensor
@@ -258,7 +262,8 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
     bool vk = config().dp_vk && !with_noise && R == 0 && S <= 256 && ld % 4 == 0 &&
               (reinterpret_cast<uintptr_t>(neg_cent) & 15) == 0 && dp_chunk_rows(S) == 32 &&
               (dp_team_warps(S) == 2 || (S + 127) / 128 == 2);   // 4 value warps: C = 2 columns per thread only
-    if (vk) vk = dp_make_plan(pl, B, T, S, ld, 0, 0, smem_budget ? smem_budget : (size_t)kSmemBudget, false, true);
+    if (vk) vk = dp_make_plan(pl, B, T, S, ld, 0, 0, smem_budget ? smem_budget : (size_t)kSmemBudget, false, true, help);
+    if (help > 0 && !vk) return MAS_ERR_UNSUPPORTED_SHAPE;   // the helper warps come with the value / origin split
     if (!vk && !dp_make_plan(pl, B, T, S, ld, config().dp_stages, R,
                              smem_budget ? smem_budget : (size_t)kSmemBudget, with_noise, false))
         return MAS_ERR_UNSUPPORTED_SHAPE;

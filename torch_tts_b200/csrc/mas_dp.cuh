@@ -44,6 +44,7 @@ constexpr int kDpBar = 3;     // named barrier of the DP role (kThreads threads)
 constexpr int kZeroBytes = 8192;  // zeroed shared buffer the path zero-fill bulk-stores from
 constexpr uint32_t kZeroFillBuf = 32768;  // zero page of the zero-fill role (contraction CTAs that ran out of tiles)
 constexpr int kZeroParts = 8;             // slices per path plane handed out by the zero-fill role
+constexpr int kHelpAhead = 4;             // noise chunks kept ahead in L2 by the helpers
 
 // mel rows per chunk (= per TMA tile) for S text columns: a stage stays <= 32 KB
 constexpr int kBitsPad = 4;   // words between decision-word rows beyond S_pad (keeps 16-byte alignment)
@@ -75,6 +76,8 @@ struct DpParams {
     int R;       // mel rows per chunk (template parameter of the role; 32, 16 or 8)
     int W;       // DP warps per team (template parameter of the role; 2 or 4)
     int vk;      // value / origin warp split (W value warps + W origin warps + producer)
+    int help;    // noise-helper warps behind the producer warp (fused noise kernel): they add (std * noise) * scale to
+                 // every cost tile in shared memory one chunk step ahead of the value warps
     int stages;  // cost-tile ring depth (2..kMaxStages)
     int path_dtype;
     int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads,
@@ -382,7 +385,7 @@ __device__ __forceinline__ int check_row(int j) { return j == 0 ? 0 : kCheck * j
 // named barrier `bar`; the standalone kernel runs one team per CTA, the fused kernel up to two.
 __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *smem, int tid, int bar)
 {
-    const int nthr = dp_threads(p.W, p.vk != 0);
+    const int nthr = dp_threads(p.W, p.vk != 0) + 32 * p.help;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
     float *bnd_v = reinterpret_cast<float *>(smem + p.off_bnd_v);
     int *bnd_o = reinterpret_cast<int *>(smem + p.off_bnd_o);
@@ -401,10 +404,97 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
     bar_sync(bar, nthr);
 }
 
+// The noise-helper warps of a DP team (fused noise kernel; dp_role with kHelp > 0).  VITS2 aligns
+// neg_cent + (std * randn) * scale (models.py:1241-1247); the helpers add that term to every cost tile IN PLACE in
+// shared memory one chunk step ahead of the value warps, which therefore run the plain body.
+//   * The draw comes straight from global memory into registers (no shared-memory staging: a staged copy made
+//     the chunk step shared-memory-bandwidth bound -- 200 KB per 32 rows through one SM's 128 B / clock).
+//   * Two warp groups take alternate chunks: a group issues the loads of its next chunk right after it has
+//     applied the current one and then sits out a step, so a load has two chunk steps (~2 us) to land and only
+//     one generation of loads is ever in flight per warp (two generations in one warp -- double-buffered
+//     registers -- serialised on the scoreboard and exposed the full HBM latency every step).
+//   * A separate function on purpose: its 64 load registers must not weigh on the register allocation of the
+//     value warps' loop.
+template <int R, int kHelp>
+__device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *smem, int b, int hw, int lane, uint32_t g0,
+                                             int n_chunks, int n_steps, int t_y, int bar, int nthreads)
+{
+    static_assert(kHelp >= 2 && kHelp % 2 == 0, "two warp groups");
+    constexpr int HT = 32 * (kHelp / 2);                 // threads of a group
+    constexpr int KH = (R * 64 + HT - 1) / HT;           // 16-byte items per thread and chunk at the widest plane (256 floats)
+    const int grp = hw & 1, gl = (hw >> 1) * 32 + lane;
+    const int ld4 = p.ld >> 2;                            // (ld == S: 16-byte rows, checked by the launcher)
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    const size_t plane = (size_t)p.T * p.S;
+    const float4 *nz4 = reinterpret_cast<const float4 *>(p.noise + (size_t)b * plane) + gl;
+    // unbiased std over ALL cells, padding included (torch.std default, models.py:1243), from fp64 sums
+    float sd;
+    {
+        const double n = (double)p.B * (double)plane;
+        const double s0 = __ldcg(p.stats), s1 = __ldcg(p.stats + 1);
+        const double mean = s0 / n;
+        double var = (s1 - s0 * mean) / (n > 1.0 ? n - 1.0 : 1.0);
+        if (var < 0) var = 0;
+        sd = (float)sqrt(var);
+    }
+    const float scale = p.noise_scale;
+    const uint32_t n_stages = (uint32_t)p.stages;
+    float4 nr[KH];
+    long long hacc[2] = {0, 0};  // diagnostics: cycles waiting for the cost tile, applying
+    auto load = [&](int c) {
+        if (c >= n_chunks) return;
+        const int n4 = min(R, t_y - c * R) * ld4;
+        const float4 *src = nz4 + (size_t)c * R * ld4;
+#pragma unroll
+        for (int k = 0; k < KH; ++k)
+            if (gl + k * HT < n4) nr[k] = __ldcs(src + k * HT);
+        // this group's chunk after that one: into L2, one 128-byte line per thread and pass
+        const int cp = c + 2;
+        if (cp < n_chunks) {
+            const char *pb = reinterpret_cast<const char *>(nz4 - gl + (size_t)cp * R * ld4);
+            const int pbytes = min(R, t_y - cp * R) * ld4 * 16;
+            for (int o = gl * 128; o < pbytes; o += HT * 128) prefetch_l2(pb + o);
+        }
+    };
+    load(grp);
+    for (int step = 0; step < n_steps; ++step) {
+        const int c = step;
+        if ((c & 1) == grp && c < n_chunks) {
+            const int n4 = min(R, t_y - c * R) * ld4;
+            const uint32_t g = g0 + (uint32_t)c;
+            const uint32_t st = g % n_stages, st_par = (g / n_stages) & 1u;
+            float4 *t4 = reinterpret_cast<float4 *>(smem + p.off_stage + (size_t)st * p.stage_bytes) + gl;
+            const long long h0 = MAS_TR(p) ? clock64() : 0;
+            mbar_wait(&full[st], st_par);
+            const long long h1 = MAS_TR(p) ? clock64() : 0;
+#pragma unroll
+            for (int k = 0; k < KH; ++k)
+                if (gl + k * HT < n4) {
+                    float4 cv = t4[k * HT];
+                    cv.x = __fadd_rn(cv.x, __fmul_rn(__fmul_rn(sd, nr[k].x), scale));
+                    cv.y = __fadd_rn(cv.y, __fmul_rn(__fmul_rn(sd, nr[k].y), scale));
+                    cv.z = __fadd_rn(cv.z, __fmul_rn(__fmul_rn(sd, nr[k].z), scale));
+                    cv.w = __fadd_rn(cv.w, __fmul_rn(__fmul_rn(sd, nr[k].w), scale));
+                    t4[k * HT] = cv;
+                }
+            // generic stores into a stage the bulk-copy engine overwrites a few steps from now: order them for
+            // the async proxy here, where there is slack
+            fence_proxy_async();
+            if (MAS_TR(p)) hacc[0] += h1 - h0, hacc[1] += clock64() - h1;
+            load(c + 2);
+        }
+        bar_sync(bar, nthreads);
+    }
+    if (MAS_TR(p) && gl == 0 && grp == 0)
+        for (int j = 0; j < 2; ++j) p.trace[40960 + (size_t)b * 16 + 12 + j] = (unsigned long long)hacc[j];
+}
+
 // Aligns utterance b.  Runs on the dp_threads(W) threads of one team; `slot` selects the team's region of
 // the spill workspace; g_base is the running cost-tile counter of this CTA's stage ring (mbarrier phases
 // continue across utterances).
-template <int C, int R, int W, bool kVec, bool kNoise = false, bool kVK = false>
+// kHelp > 0: that many helper warps sit behind the producer warp and add VITS2's noise to every cost tile one chunk
+// step ahead of the value warps (dp_noise_helper).
+template <int C, int R, int W, bool kVec, bool kNoise = false, bool kVK = false, int kHelp = 0>
 __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
                                         int bar)
 {
@@ -415,9 +505,11 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     constexpr int S_pad = W * 32 * C;
     constexpr int S_bits = S_pad + kBitsPad;
     static_assert(!kVK || R == kCheck, "the warp split replays whole decision words: one chunk = one word");
-    constexpr int kThreads = dp_threads(W, kVK);
+    static_assert(kHelp == 0 || (kVec && !kNoise), "helper warps work on 16-byte rows and replace the in-loop noise");
+    constexpr int kThreads = dp_threads(W, kVK) + 32 * kHelp;
     constexpr int kDpWarps = W;                       // warps that consume cost tiles
     constexpr int kProducerWarp = kVK ? 2 * W : W;
+    constexpr int kHs = kHelp > 0 ? 1 : 0;            // the value warps trail the helpers by one chunk step
     const int esize = path_elem_size(p.path_dtype);
     const size_t plane = (size_t)T * S;
     unsigned char *path_b = p.path ? p.path + (size_t)b * plane * esize : nullptr;
@@ -477,7 +569,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
 
     if (MAS_TR(p) && tid == 0) p.trace[12288 + (size_t)b * 32 + 0] = globaltimer_ns();
     const int n_chunks = (t_y + R - 1) / R;
-    const int n_steps = n_chunks + kDpWarps - 1 + (kVK ? 1 : 0);  // the bookkeeping warps trail by one step
+    const int n_steps = n_chunks + kDpWarps - 1 + (kVK ? 1 : 0) + kHs;  // the bookkeeping warps trail by one step
     const size_t utt_elem0 = (size_t)b * T * ld;  // first element of this utterance's cost plane
     const size_t total_bytes = (size_t)p.B * T * ld * 4;
 
@@ -489,7 +581,9 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         bool saw_nonfinite = false;
         if (warp == kProducerWarp) {
             // =================== producer warp ===================
+            long long iacc[3] = {0, 0, 0};  // diagnostics: cycles in flag wait + pad stores + fence, arrive, bulk issue
             auto issue_tile = [&](int c) {
+                const long long i0 = MAS_TR(p) ? clock64() : 0;
                 const uint32_t g = g0 + c;
                 const uint32_t st = g % n_stages;
                 const int row0 = c * R;
@@ -520,6 +614,15 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                             (o < want) ? *reinterpret_cast<const float *>(src + o) : 0.0f;
                 }
                 if MAS_DBG(p, 4) bulk = 0;
+                const long long i1 = MAS_TR(p) ? clock64() : 0;
+                if (!kNoise && MAS_TR(p)) {
+                    mbar_arrive_expect_tx(&full[st], bulk);
+                    const long long i2 = clock64();
+                    if (bulk) bulk_g2s(dst, src, bulk, &full[st]);
+                    const long long i3 = clock64();
+                    iacc[0] += i1 - i0, iacc[1] += i2 - i1, iacc[2] += i3 - i2;
+                    return;
+                }
                 if (kNoise) {
                     // the noise tile of the same cells, nz_off behind the cost tile (same padding / tail rules)
                     unsigned char *ndst = dst + p.noise_off;
@@ -567,16 +670,25 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                 const long long q1 = MAS_TR(p) ? clock64() : 0;
                 bar_sync(bar, kThreads);
                 const long long q2 = MAS_TR(p) ? clock64() : 0;
-                const int freed = step - (kDpWarps - 1);
+                const int freed = step - (kDpWarps - 1) - kHs;
                 if (lane == 0 && freed >= 0 && freed + (int)n_stages < n_chunks) issue_tile(freed + (int)n_stages);
+                __syncwarp();
                 if (MAS_TR(p)) {
                     const long long q3 = clock64();
                     pacc[0] += q1 - q0, pacc[1] += q2 - q1, pacc[2] += q3 - q2;
                 }
             }
-            if (MAS_TR(p) && lane == 0)
+            if (MAS_TR(p) && lane == 0) {
                 for (int j = 0; j < 3; ++j) p.trace[40960 + (size_t)b * 16 + 8 + j] = (unsigned long long)pacc[j];
+                p.trace[40960 + (size_t)b * 16 + 11] = (unsigned long long)iacc[0];
+                p.trace[40960 + (size_t)b * 16 + 14] = (unsigned long long)iacc[1];
+                p.trace[40960 + (size_t)b * 16 + 15] = (unsigned long long)iacc[2];
+            }
             if (pass == 0 && bulk_ok && lane == 0) bulk_wait_all();  // zeros land before the ones are scattered
+        } else if (kHelp > 0 && warp > kProducerWarp) {
+            // =================== noise helpers: chunk `step` while the value warps are on chunk step - 1 ===================
+            dp_noise_helper<R, (kHelp > 0 ? kHelp : 2)>(p, smem, b, warp - kProducerWarp - 1, lane, g0, n_chunks, n_steps, t_y,
+                                                      bar, kThreads);
         } else if (kVK && warp >= W) {
             // =================== origin warps (warp split), one step behind their value warp ===================
             // The value warps leave the decision word of every cell; these warps replay it into the
@@ -593,7 +705,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             const int edge_rows = (w + 1) * 32 * C;
             long long kacc[2] = {0, 0};  // diagnostics: cycles in compute, barrier
             for (int step = 0; step < n_steps; ++step) {
-                const int c = step - w - 1;
+                const int c = step - w - 1 - kHs;
                 const long long f0 = MAS_TR(p) ? clock64() : 0;
                 long long f1 = f0;
                 if (c >= 0 && c < n_chunks && !MAS_DBG(p, 16)) {
@@ -656,7 +768,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
             long long dacc[4] = {0, 0, 0, 0};  // diagnostics: cycles in tile wait, compute, bits/hop, barrier
             uint32_t st = g0 % n_stages, st_par = (g0 / n_stages) & 1u;  // stage / mbarrier parity of chunk 0, then stepped
             for (int step = 0; step < n_steps; ++step) {
-                const int c = step - w;
+                const int c = step - w - kHs;
                 long long d0 = MAS_TR(p) ? clock64() : 0, d1 = d0, d2 = d0, d3 = d0;
                 if (c >= 0 && c < n_chunks) {
                     const int row0 = c * R;
@@ -900,6 +1012,6 @@ size_t dp_workspace_bytes(int B, int T, int S);
 int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out,
                int path_dtype, int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace,
                size_t workspace_bytes, int B, int T, int S, int32_t **order_out, int R, size_t smem_budget,
-               bool with_noise = false, int ld = 0);
+               bool with_noise = false, int ld = 0, int help = 0);
 
 }  // namespace mas

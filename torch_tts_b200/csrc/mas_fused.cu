@@ -12,11 +12,12 @@
 //
 // VITS2 noise-scaled MAS (models.py:1241-1247) -- mas_fused_noise_kernel:
 // the standard deviation over ALL cost cells has to exist before the first DP row, so the kernel has two phases
-// around a grid barrier: (1) every CTA contracts, the epilogue also accumulates sum / sum of squares; (2) the
-// first n_dp CTAs run the DP exactly as above, the others first add (std * noise) * scale to the L2-resident
-// cost plane tile by tile in mel-tile-major order (raising the same per-tile flags the DP waits on), then
-// zero-fill the path planes.  The DP warps therefore run the plain (no-noise) body; the noise draw is read
-// once from HBM by CTAs that would otherwise idle.
+// around a grid barrier: (1) every CTA contracts, the epilogue also accumulates sum / sum of squares; (2) up to
+// one DP CTA per utterance runs the DP as above.  Eight helper warps of each DP CTA add (std * noise) * scale to
+// the cost tiles in shared memory one chunk step ahead of the value warps (dp_role, kHelp), which therefore run
+// the plain body; the draw is read once from HBM, by the SM that needs it.  (A first version applied the noise
+// from the idle CTAs to the L2-resident plane: 393 KB through one SM per 128-row tile, ~7 us each -- the DP
+// waited for its tiles and the step took 141 us at config 2.)
 //
 // The private cost plane has its own row stride (S rounded up to 4 floats), so S and T are arbitrary.
 #include <atomic>
@@ -31,22 +32,21 @@ struct FusedParams {
     TcParams tc;
     DpParams dp;
     int n_dp;              // the first n_dp CTAs turn into DP CTAs after their share of the contraction
-    // noise kernel only
-    const float *noise;    // [B][T][S] draw standing in for torch.randn_like(neg_cent)
-    float noise_scale;
-    uint32_t *grid_bar;    // grid barrier counter (cleared with the flags)
+    uint32_t *grid_bar;    // noise kernel: grid barrier counter (cleared with the flags)
 };
 
-template <int C, int R, int W, bool kVK>
+constexpr int kNoiseHelpWarps = 8;   // helper warps of a DP CTA in the noise kernel (dp_role, kHelp)
+
+template <int C, int R, int W, bool kVK, int kHelp = 0>
 __device__ __forceinline__ void fused_dp_ctas(const FusedParams &fp, unsigned char *smem)
 {
-    // DP CTA j aligns utterances j, j + n_dp, ... on its first dp_threads(W) threads
-    if ((int)threadIdx.x >= dp_threads(W, kVK)) return;
+    // DP CTA j aligns utterances j, j + n_dp, ... on its first dp_threads(W) (+ helper) threads
+    if ((int)threadIdx.x >= dp_threads(W, kVK) + 32 * kHelp) return;
     const int j = (int)blockIdx.x;
     uint32_t g_base = 0;
     dp_role_init(fp.dp, smem, threadIdx.x, kDpBar);
     for (int b = j; b < fp.dp.B; b += fp.n_dp)
-        dp_role<C, R, W, true, false, kVK>(fp.dp, smem, b, j, g_base, threadIdx.x, kDpBar);
+        dp_role<C, R, W, true, false, kVK, kHelp>(fp.dp, smem, b, j, g_base, threadIdx.x, kDpBar);
 }
 
 template <int C, int R, int W, bool kPair, bool kVK>
@@ -93,64 +93,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_c
 #endif
 
 // ---------------------------------------------------------------------------
-// noise-scaled alignment: contraction + statistics | grid barrier | noise appliers + DP + zero fill
+// noise-scaled alignment: contraction + statistics | grid barrier | DP (noise applied by helper warps) + zero fill
 // ---------------------------------------------------------------------------
-// Adds (sd * noise) * scale to the private cost plane, one 128-row mel tile of one utterance at a time, items
-// in mel-tile-major order strided over the applier CTAs; raises the tile's flag when its rows are in memory.
-// Rounded after every operation like the reference's `std * randn * scale` then `+` (models.py:1242-1247).
-__device__ __forceinline__ void noise_apply_role(const FusedParams &fp, float sd, int rank, int n_appliers)
-{
-    const TcParams &tc = fp.tc;
-    const int T = tc.T, S = tc.S, ld = tc.ld, m_tiles = tc.m_tiles;
-    const int n_items = tc.B * m_tiles;
-    const float scale = fp.noise_scale;
-    const bool vec = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(fp.noise) & 15) == 0);   // (then ld == S)
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int item = rank; item < n_items; item += n_appliers) {
-        const int mt = item / tc.B, b = item - mt * tc.B;
-        const int t_y = fp.dp.t_ys[b];
-        const int r0 = mt * kBM;
-        int r1 = min(r0 + kBM, T);
-        if (t_y >= 1 && t_y <= T) r1 = min(r1, t_y);   // rows past t_y are never read by the DP
-        if (r0 >= r1) continue;
-        float *nc = tc.out + ((size_t)b * T + r0) * ld;
-        const float *nz = fp.noise + ((size_t)b * T + r0) * S;
-        if (vec) {
-            const int n4 = (r1 - r0) * S / 4;
-            float4 *nc4 = reinterpret_cast<float4 *>(nc);
-            const float4 *nz4 = reinterpret_cast<const float4 *>(nz);
-            for (int i = tid; i < n4; i += 4 * nthr) {
-                float4 c[4], n[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i + u * nthr < n4) {
-                        c[u] = __ldcg(nc4 + i + u * nthr);     // L2 (written by other SMs' TMA stores)
-                        n[u] = __ldcs(nz4 + i + u * nthr);     // streamed once from HBM
-                    }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i + u * nthr < n4) {
-                        c[u].x = __fadd_rn(c[u].x, __fmul_rn(__fmul_rn(sd, n[u].x), scale));
-                        c[u].y = __fadd_rn(c[u].y, __fmul_rn(__fmul_rn(sd, n[u].y), scale));
-                        c[u].z = __fadd_rn(c[u].z, __fmul_rn(__fmul_rn(sd, n[u].z), scale));
-                        c[u].w = __fadd_rn(c[u].w, __fmul_rn(__fmul_rn(sd, n[u].w), scale));
-                        __stcg(nc4 + i + u * nthr, c[u]);
-                    }
-            }
-        } else {
-            const int n = (r1 - r0) * S;
-            for (int i = tid; i < n; i += nthr) {
-                const int r = i / S, x = i - r * S;
-                float *q = nc + (size_t)r * ld + x;
-                *q = __fadd_rn(__ldcg(q), __fmul_rn(__fmul_rn(sd, __ldcs(nz + i)), scale));
-            }
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release_gpu(fp.dp.flags + (size_t)b * m_tiles + mt, 1u);
-    }
-}
-
 template <int C, int R, int W, bool kVK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     mas_fused_noise_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CUtensorMap tm_z,
@@ -158,8 +102,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     // phase 1: the whole batch's cost plane + its statistics (no tile flags: nothing may be aligned yet)
+    if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + blockIdx.x] = globaltimer_ns();  // CTA entry
     cost_tc_role<true, true>(fp.tc, &tm_z, &tm_out, smem, blockIdx.x >> 1, gridDim.x >> 1);
-    // grid barrier: every CTA's tiles are in memory and its partial sums are in stats[]
+    if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 256 + blockIdx.x] = globaltimer_ns();  // contraction done
+    // grid barrier: every CTA's tiles are in memory (L2) and its partial sums are in stats[]
     fence_proxy_async_all();
     __threadfence();
     __syncthreads();
@@ -168,21 +114,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         atomicAdd(fp.grid_bar, 1u);
         while (ld_acquire_gpu(fp.grid_bar) < gridDim.x) __nanosleep(32);
         __threadfence();
+        fence_proxy_async_all();   // the DP's bulk copies (async proxy) read what other SMs' bulk stores wrote
     }
     __syncthreads();
+    if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 512 + blockIdx.x] = globaltimer_ns();  // barrier passed
     if ((int)blockIdx.x >= fp.n_dp) {
-        // unbiased std over ALL cells, padding included (torch.std default, models.py:1243), from fp64 sums
-        const double *st = fp.tc.stats;
-        const double n = (double)fp.tc.B * (double)fp.tc.T * (double)fp.tc.S;
-        const double s0 = __ldcg(st), s1 = __ldcg(st + 1);
-        const double mean = s0 / n;
-        double var = (s1 - s0 * mean) / (n > 1.0 ? n - 1.0 : 1.0);
-        if (var < 0) var = 0;
-        noise_apply_role(fp, (float)sqrt(var), (int)blockIdx.x - fp.n_dp, (int)gridDim.x - fp.n_dp);
         if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem);
+        if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 1024 + blockIdx.x] = globaltimer_ns();  // zero fill done
         return;
     }
-    fused_dp_ctas<C, R, W, kVK>(fp, smem);
+    // phase 2: the DP; the helper warps of every DP CTA add (std * noise) * scale to its cost tiles in shared
+    // memory, so the value warps run the plain body and the draw is read exactly once
+    fused_dp_ctas<C, R, W, kVK, kNoiseHelpWarps>(fp, smem);
 }
 
 // the private cost plane keeps 16-byte rows whatever S is
@@ -195,14 +138,10 @@ bool fused_supported(int B, int D, int T, int S)
     return cost_tc_supported(B, D, T, S) && S <= kNMax;
 }
 
-// noise-scaled alignment in one kernel: the DP CTAs need at least as many noise-applier CTAs next to them
+// noise-scaled alignment in one kernel (any batch size: the DP CTAs apply the noise themselves)
 bool fused_noise_supported(int B, int D, int T, int S)
 {
-    if (!config().noise_fused || !fused_supported(B, D, T, S)) return false;
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return 2 * B <= (sms & ~1);
+    return config().noise_fused && fused_supported(B, D, T, S) && config().dp_vk;
 }
 
 // tile flags [B][m_tiles], the zero-fill flags [B], the zero-fill queue counter, the grid barrier counter
@@ -222,25 +161,26 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const Config &cf = config();
+    // the DP CTAs stream the noise draw with 16-byte bulk copies
+    if (noise && ((S & 3) != 0 || (reinterpret_cast<uintptr_t>(noise) & 15) != 0)) return kFusedFallback;
     const int m_tiles = (T + kBM - 1) / kBM;
     const int ld = padded_ld(S);
     const int n_flags = B * (m_tiles + 1) + 2;
+    // the DP plan first: nothing has been launched yet if it turns out not to fit
+    DpPlan dp;
+    int rc = dp_prepare(dp, plane, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T,
+                        S, nullptr, 0, 0, false, ld, noise ? kNoiseHelpWarps : 0);
+    if (rc) return noise ? kFusedFallback : rc;
     TcPlan tc;
     // mel tiles wholly past t_y are skipped (the plane is private scratch) unless the noise statistics need them
-    int rc = cost_tc_prepare(tc, z_p, m_p, logs_p, plane, noise ? stats : nullptr, noise ? nullptr : t_ys, cost_ws,
-                             cost_ws_bytes, B, D, T, S, flags, n_flags, stream, ld);
+    rc = cost_tc_prepare(tc, z_p, m_p, logs_p, plane, noise ? stats : nullptr, noise ? nullptr : t_ys, cost_ws,
+                         cost_ws_bytes, B, D, T, S, flags, n_flags, stream, ld);
     if (rc) return rc;
     if (cf.stage == 1) return MAS_OK;   // prior preparation only (bench.py times it alone)
     if (!tc.p.out_tma) return kFusedFallback;
-    DpPlan dp;
-    rc = dp_prepare(dp, plane, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T,
-                    S, nullptr, 0, 0, false, ld);
-    if (rc) return rc;
     FusedParams fp{};
     fp.tc = tc.p;
     fp.dp = dp.p;
-    fp.noise = noise;
-    fp.noise_scale = noise_scale;
     const bool pair = noise ? true : cost_tc_pair_enabled();
     const int per = pair ? 2 : 1;
 
@@ -317,7 +257,7 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     };
     int n_dp = cf.fused_dp_ctas, best_k = 0;
     if (noise) {
-        n_dp = legal(B);             // fused_noise_supported(): at least as many appliers as DP CTAs
+        n_dp = B < grid ? B : grid;  // after the barrier every CTA is free: one utterance per CTA as far as they go
         best_k = 1 << 28;            // nobody leaves the contraction before the barrier
     } else if (n_dp > 0) {
         n_dp = legal(n_dp);
@@ -335,8 +275,15 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     fp.tc.seq_k = (!noise && cf.fused_rounds >= 0) ? cf.fused_rounds : best_k;
     fp.tc.seq_pure0 = noise ? 0 : n_dp / per;
     fp.tc.wave = noise ? B : fp.n_dp;
-    fp.tc.flags = noise ? nullptr : flags;    // noise: the appliers raise the flags, not the epilogue
-    fp.dp.flags = flags;
+    fp.tc.flags = noise ? nullptr : flags;    // noise: the whole plane exists before the first DP row (grid barrier)
+    fp.dp.flags = noise ? nullptr : flags;
+    if (noise) {
+        if (!dp.p.vk) return kFusedFallback;   // the helper warps come with the value / origin split
+        fp.dp.noise = noise;
+        fp.dp.stats = stats;
+        fp.dp.noise_scale = noise_scale;
+        fp.dp.help = kNoiseHelpWarps;
+    }
     fp.tc.trace = trace_buffer();
     fp.dp.trace = fp.tc.trace;
     fp.dp.flag_tiles = m_tiles;
