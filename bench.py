@@ -33,7 +33,7 @@ COST_FLOPS = 4 * T * S * D                                  # two K=D contractio
 NOISE_BYTES = FUSED_BYTES + 4 * T * S                       # + the randn_like draw (models.py:1244)
 COMPACT_BYTES = FUSED_BYTES - 4 * T * S + 4 * (T + S)       # no dense path: idx [T] + durations [S] instead
 CPU_BASELINE_REPS = 120                                     # ~10 s of host work at ~90 ms per batch
-REGIONS = 5                                                 # timed regions of K steps each; the median is reported
+REGIONS = 41                                                # timed regions of exactly K steps each; the median is reported
 WORKLOAD = "fused neg_cent+MAS, B=64 per GPU, T_text=256, T_mel=1024, D=192 (BASELINE configs[1])"
 
 
@@ -69,7 +69,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None

@@ -31,6 +31,8 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int ld, int W, int C, int R, int stag
     off = align_up(off, 128);
     p.off_stage = (uint32_t)off;
     off += (size_t)stages * p.stage_bytes;
+    p.off_nz = (uint32_t)off;                                  // helper warps: one chunk of the noise draw
+    if (help > 0) off += align_up((size_t)R * ld * 4, 128);
     p.help = help;
     p.off_bnd_v = (uint32_t)off;
     off += (size_t)(W + 1) * 2 * R * 4;

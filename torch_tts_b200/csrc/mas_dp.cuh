@@ -83,6 +83,7 @@ struct DpParams {
     int debug;   // MAS_DP_DEBUG bit mask (timing experiments): 1 no zero fill, 2 no forward compute, 4 no cost loads,
                  // 16 / 32 warp split: bookkeeping / value warps idle
     int bits_in_smem, hop_in_smem;
+    uint32_t off_nz;   // helper warps: the one-chunk noise buffer (behind the cost stages)
     uint32_t off_bits, off_hop, off_stage, stage_bytes, off_bnd_v, off_bnd_o, off_idx, off_end, off_entry, off_bar, off_zero, off_misc;
     unsigned long long bits_words_per_cta, hop_bytes_per_cta;
 };
@@ -392,6 +393,11 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
     unsigned char *zero_s = smem + p.off_zero;
     if (tid == 0) {
         for (int s = 0; s < kMaxStages; ++s) mbar_init(&full[s], 1);
+        if (p.help > 1)
+            for (int h = 0; h < 2; ++h) {
+                mbar_init(&full[kMaxStages + h], 1);                 // nfull: noise half landed
+                mbar_init(&full[kMaxStages + 2 + h], p.help - 1);    // nfree: read by every applier warp
+            }
         fence_mbar_init();
     }
     // ring 0 stands in for "the warp left of warp 0": column -1 is the -1e9 sentinel (core.pyx:24)
@@ -407,26 +413,60 @@ __device__ __forceinline__ void dp_role_init(const DpParams &p, unsigned char *s
 // The noise-helper warps of a DP team (fused noise kernel; dp_role with kHelp > 0).  VITS2 aligns
 // neg_cent + (std * randn) * scale (models.py:1241-1247); the helpers add that term to every cost tile IN PLACE in
 // shared memory one chunk step ahead of the value warps, which therefore run the plain body.
-//   * The draw comes straight from global memory into registers (no shared-memory staging: a staged copy made
-//     the chunk step shared-memory-bandwidth bound -- 200 KB per 32 rows through one SM's 128 B / clock).
-//   * Two warp groups take alternate chunks: a group issues the loads of its next chunk right after it has
-//     applied the current one and then sits out a step, so a load has two chunk steps (~2 us) to land and only
-//     one generation of loads is ever in flight per warp (two generations in one warp -- double-buffered
-//     registers -- serialised on the scoreboard and exposed the full HBM latency every step).
-//   * A separate function on purpose: its 64 load registers must not weigh on the register allocation of the
-//     value warps' loop.
+//   * The last helper warp is the noise producer: it streams the draw into a one-chunk shared buffer in two halves
+//     of R/2 rows (bulk copies, nfull[h]); the other warps add (std * noise) * scale to the cost tile and hand each
+//     half back (nfree[h]) as soon as they have read it, so the next chunk's half is on its way while this step
+//     is still running.  (Its own warp: on the cost-tile producer's lane the two waits sat behind ~1300 cycles of
+//     tile issue and every step paid for both.)
+//   * Loads and stores are batched by hand (all loads of a half, then the arithmetic, then the stores): the
+//     compiler must assume that the tile and the noise buffer alias and would otherwise serialise item by item.
+//   * Tried and dropped: the draw straight from global memory into registers (no shared buffer).  One chunk ahead
+//     with double-buffered registers serialised on the scoreboard; two warp groups on alternate chunks still saw
+//     the loads arrive late; both ran 4600-5100 cycles per chunk step against 3100 for this version.
+//   * A separate function on purpose: its registers must not weigh on the allocation of the value warps' loop.
 template <int R, int kHelp>
 __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *smem, int b, int hw, int lane, uint32_t g0,
                                              int n_chunks, int n_steps, int t_y, int bar, int nthreads)
 {
-    static_assert(kHelp >= 2 && kHelp % 2 == 0, "two warp groups");
-    constexpr int HT = 32 * (kHelp / 2);                 // threads of a group
-    constexpr int KH = (R * 64 + HT - 1) / HT;           // 16-byte items per thread and chunk at the widest plane (256 floats)
-    const int grp = hw & 1, gl = (hw >> 1) * 32 + lane;
-    const int ld4 = p.ld >> 2;                            // (ld == S: 16-byte rows, checked by the launcher)
+    static_assert(kHelp >= 2, "one producer warp + at least one applier warp");
+    constexpr int HT = 32 * (kHelp - 1);                      // applier threads
+    constexpr int KQ = ((R / 2) * 64 + HT - 1) / HT;          // 16-byte items per applier and half at the widest plane (256 floats)
+    const int ld = p.ld, ld4 = ld >> 2;                       // (ld == S: 16-byte rows, checked by the launcher)
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *nfull = full + kMaxStages;      // [2] noise half landed
+    uint64_t *nfree = full + kMaxStages + 2;  // [2] noise half read by all applier warps
     const size_t plane = (size_t)p.T * p.S;
-    const float4 *nz4 = reinterpret_cast<const float4 *>(p.noise + (size_t)b * plane) + gl;
+    const uint32_t n_stages = (uint32_t)p.stages;
+    const uint32_t half_bytes = (uint32_t)(R / 2) * ld * 4;
+
+    if (hw == kHelp - 1) {
+        // ---- noise producer ----
+        const unsigned char *nz_b = reinterpret_cast<const unsigned char *>(p.noise + (size_t)b * plane);
+        auto issue = [&](int c) {
+            if (c >= n_chunks) return;
+            const uint32_t g = g0 + (uint32_t)c;
+            const int rows = min(R, t_y - c * R);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int rows_h = h == 0 ? min(rows, R / 2) : max(rows - R / 2, 0);
+                const uint32_t bytes = (uint32_t)rows_h * ld * 4;
+                mbar_wait(&nfree[h], (g & 1u) ^ 1u);              // every applier warp has read the previous contents
+                mbar_arrive_expect_tx(&nfull[h], bytes);          // (an empty half still completes its phase)
+                if (bytes) bulk_g2s(smem + p.off_nz + h * half_bytes, nz_b + ((size_t)c * R + (size_t)h * (R / 2)) * ld * 4, bytes, &nfull[h]);
+            }
+        };
+        if (lane == 0) issue(0);
+        __syncwarp();
+        for (int step = 0; step < n_steps; ++step) {
+            if (lane == 0) issue(step + 1);   // follows the appliers through chunk `step`
+            __syncwarp();
+            bar_sync(bar, nthreads);
+        }
+        return;
+    }
+
+    // ---- appliers ----
+    const int gl = hw * 32 + lane;
     // unbiased std over ALL cells, padding included (torch.std default, models.py:1243), from fp64 sums
     float sd;
     {
@@ -438,55 +478,66 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
         sd = (float)sqrt(var);
     }
     const float scale = p.noise_scale;
-    const uint32_t n_stages = (uint32_t)p.stages;
-    float4 nr[KH];
-    long long hacc[2] = {0, 0};  // diagnostics: cycles waiting for the cost tile, applying
-    auto load = [&](int c) {
+    // the draw a few chunks ahead: into L2, one 128-byte line per thread and pass
+    const char *nz_c = reinterpret_cast<const char *>(p.noise + (size_t)b * plane);
+    auto prefetch_chunk = [&](int c) {
         if (c >= n_chunks) return;
-        const int n4 = min(R, t_y - c * R) * ld4;
-        const float4 *src = nz4 + (size_t)c * R * ld4;
-#pragma unroll
-        for (int k = 0; k < KH; ++k)
-            if (gl + k * HT < n4) nr[k] = __ldcs(src + k * HT);
-        // this group's chunk after that one: into L2, one 128-byte line per thread and pass
-        const int cp = c + 2;
-        if (cp < n_chunks) {
-            const char *pb = reinterpret_cast<const char *>(nz4 - gl + (size_t)cp * R * ld4);
-            const int pbytes = min(R, t_y - cp * R) * ld4 * 16;
-            for (int o = gl * 128; o < pbytes; o += HT * 128) prefetch_l2(pb + o);
-        }
+        const char *pb = nz_c + (size_t)c * R * ld * 4;
+        const int pbytes = min(R, t_y - c * R) * ld * 4;
+        for (int o = gl * 128; o < pbytes; o += HT * 128) prefetch_l2(pb + o);
     };
-    load(grp);
+    for (int c = 1; c <= kHelpAhead; ++c) prefetch_chunk(c);
+    long long hacc[3] = {0, 0, 0};  // diagnostics: cycles waiting for the cost tile, for the noise halves, applying
     for (int step = 0; step < n_steps; ++step) {
         const int c = step;
-        if ((c & 1) == grp && c < n_chunks) {
-            const int n4 = min(R, t_y - c * R) * ld4;
+        if (c < n_chunks) {
+            prefetch_chunk(c + 1 + kHelpAhead);
+            const int rows = min(R, t_y - c * R);
             const uint32_t g = g0 + (uint32_t)c;
-            const uint32_t st = g % n_stages, st_par = (g / n_stages) & 1u;
-            float4 *t4 = reinterpret_cast<float4 *>(smem + p.off_stage + (size_t)st * p.stage_bytes) + gl;
+            const uint32_t st = g % n_stages, st_par = (g / n_stages) & 1u, npar = g & 1u;
+            float4 *tile4 = reinterpret_cast<float4 *>(smem + p.off_stage + (size_t)st * p.stage_bytes) + gl;
             const long long h0 = MAS_TR(p) ? clock64() : 0;
             mbar_wait(&full[st], st_par);
-            const long long h1 = MAS_TR(p) ? clock64() : 0;
+            long long h1 = MAS_TR(p) ? clock64() : 0;
+            if (MAS_TR(p)) hacc[0] += h1 - h0;
 #pragma unroll
-            for (int k = 0; k < KH; ++k)
-                if (gl + k * HT < n4) {
-                    float4 cv = t4[k * HT];
-                    cv.x = __fadd_rn(cv.x, __fmul_rn(__fmul_rn(sd, nr[k].x), scale));
-                    cv.y = __fadd_rn(cv.y, __fmul_rn(__fmul_rn(sd, nr[k].y), scale));
-                    cv.z = __fadd_rn(cv.z, __fmul_rn(__fmul_rn(sd, nr[k].z), scale));
-                    cv.w = __fadd_rn(cv.w, __fmul_rn(__fmul_rn(sd, nr[k].w), scale));
-                    t4[k * HT] = cv;
+            for (int h = 0; h < 2; ++h) {
+                const int rows_h = h == 0 ? min(rows, R / 2) : max(rows - R / 2, 0);
+                const int n4 = rows_h * ld4;
+                const float4 *nz4 = reinterpret_cast<const float4 *>(smem + p.off_nz + h * half_bytes) + gl;
+                float4 *t4 = tile4 + (size_t)h * (R / 2) * ld4;
+                mbar_wait(&nfull[h], npar);
+                const long long h2 = MAS_TR(p) ? clock64() : 0;
+                float4 cv[KQ], nv[KQ];
+#pragma unroll
+                for (int k = 0; k < KQ; ++k)
+                    if (gl + k * HT < n4) cv[k] = t4[k * HT], nv[k] = nz4[k * HT];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&nfree[h]);   // this warp has read the half: the next chunk's may come
+#pragma unroll
+                for (int k = 0; k < KQ; ++k)
+                    if (gl + k * HT < n4) {
+                        cv[k].x = __fadd_rn(cv[k].x, __fmul_rn(__fmul_rn(sd, nv[k].x), scale));
+                        cv[k].y = __fadd_rn(cv[k].y, __fmul_rn(__fmul_rn(sd, nv[k].y), scale));
+                        cv[k].z = __fadd_rn(cv[k].z, __fmul_rn(__fmul_rn(sd, nv[k].z), scale));
+                        cv[k].w = __fadd_rn(cv[k].w, __fmul_rn(__fmul_rn(sd, nv[k].w), scale));
+                        t4[k * HT] = cv[k];
+                    }
+                if (MAS_TR(p)) {
+                    const long long h3 = clock64();
+                    hacc[1] += h2 - h1, hacc[2] += h3 - h2, h1 = h3;
                 }
-            // generic stores into a stage the bulk-copy engine overwrites a few steps from now: order them for
-            // the async proxy here, where there is slack
+            }
+            // generic stores into a stage the bulk-copy engine overwrites a few steps from now: order them for the
+            // async proxy here, where there is slack
             fence_proxy_async();
-            if (MAS_TR(p)) hacc[0] += h1 - h0, hacc[1] += clock64() - h1;
-            load(c + 2);
         }
         bar_sync(bar, nthreads);
     }
-    if (MAS_TR(p) && gl == 0 && grp == 0)
-        for (int j = 0; j < 2; ++j) p.trace[40960 + (size_t)b * 16 + 12 + j] = (unsigned long long)hacc[j];
+    if (MAS_TR(p) && gl == 0) {
+        p.trace[40960 + (size_t)b * 16 + 12] = (unsigned long long)(hacc[0] + hacc[1]);
+        p.trace[40960 + (size_t)b * 16 + 13] = (unsigned long long)hacc[2];
+    }
 }
 
 // Aligns utterance b.  Runs on the dp_threads(W) threads of one team; `slot` selects the team's region of
@@ -494,8 +545,12 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
 // continue across utterances).
 // kHelp > 0: that many helper warps sit behind the producer warp and add VITS2's noise to every cost tile one chunk
 // step ahead of the value warps (dp_noise_helper).
+// Not inlined on purpose: the fused kernels run this after the contraction role, whose epilogue sits at the
+// 128-register limit of a 512-thread CTA; compiled into the same function, the value warps' loop inherited that
+// pressure (thread-index values rematerialised inside the row loop) and ran 60 % slower than in the standalone
+// DP kernel.
 template <int C, int R, int W, bool kVec, bool kNoise = false, bool kVK = false, int kHelp = 0>
-__device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
+__device__ __noinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
                                         int bar)
 {
     const int warp = tid >> 5;
