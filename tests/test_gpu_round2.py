@@ -126,9 +126,7 @@ def test_noise_branch_is_two_launches_and_matches_the_separate_kernels(cuda_devi
     t_x, t_y, host, dev = _inputs(B, S, T, seed=11, ragged=ragged, dev=cuda_device)
     noise = torch.randn((B, T, S), generator=torch.Generator().manual_seed(3)).to(cuda_device)
     (a, w, (idx, dur, status)), n = _launches(lambda: tts.align(*dev, 0.01, noise, return_compact=True))
-    # (the DP CTAs stream the draw with 16-byte bulk copies: rows that are not a multiple of 16 bytes take the
-    # separate launches)
-    assert (n == 2) if S % 4 == 0 else (n >= 3), n
+    assert n == 2, n
     assert (status == 0).all() and torch.equal(dur.sum(1).cpu(), t_y)
     mas_env(MAS_NOISE_FUSED=0)
     (a3, w3, (idx3, dur3, status3)), n3 = _launches(lambda: tts.align(*dev, 0.01, noise, return_compact=True))

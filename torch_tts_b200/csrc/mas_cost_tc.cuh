@@ -354,7 +354,11 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     // Programmatic dependent launch: this grid may have started while the kernel that writes the operand
     // images, the bias partial sums and the cleared flags was still running; everything above overlapped
     // with it, everything below reads its output.  (Without such a launch the wait returns at once.)
-    if (p.pdl) {
+    // Only the roles that touch that kernel's output wait: the B producer (images), the bias warp (partial sums) and
+    // the epilogue (tile flags, cleared there).  The raw-z producer and the A converters start on the first K blocks
+    // right away, so the operand ring is already filling when the images arrive.  (Every thread of the CTA passes
+    // the role's final barrier after the B producer's wait has returned, i.e. after that grid has completed.)
+    if (p.pdl && (warp == 0 || warp == 2 || (warp >= 4 && warp < 8))) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         fence_proxy_async_all();  // the images are read through the async proxy (bulk copies)
     }

@@ -32,7 +32,7 @@ bool dp_plan_try(DpPlan &pl, int T, int S, int ld, int W, int C, int R, int stag
     p.off_stage = (uint32_t)off;
     off += (size_t)stages * p.stage_bytes;
     p.off_nz = (uint32_t)off;                                  // helper warps: one chunk of the noise draw
-    if (help > 0) off += align_up((size_t)R * ld * 4, 128);
+    if (help > 0) off += align_up((size_t)R * ld * 4 + 64, 128);   // two halves, each with room for a misaligned start
     p.help = help;
     p.off_bnd_v = (uint32_t)off;
     off += (size_t)(W + 1) * 2 * R * 4;

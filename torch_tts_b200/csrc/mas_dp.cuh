@@ -437,11 +437,13 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
     uint64_t *nfree = full + kMaxStages + 2;  // [2] noise half read by all applier warps
     const size_t plane = (size_t)p.T * p.S;
     const uint32_t n_stages = (uint32_t)p.stages;
-    const uint32_t half_bytes = (uint32_t)(R / 2) * ld * 4;
+    const uint32_t half_stride = (uint32_t)(R / 2) * ld * 4 + 32;   // room for the misaligned start and the 16-byte round-up
+    const bool nvec = (p.S & 3) == 0 && (reinterpret_cast<uintptr_t>(p.noise) & 15) == 0;   // then ld == S and every half starts aligned
 
     if (hw == kHelp - 1) {
         // ---- noise producer ----
-        const unsigned char *nz_b = reinterpret_cast<const unsigned char *>(p.noise + (size_t)b * plane);
+        const uintptr_t nz_b = reinterpret_cast<uintptr_t>(p.noise + (size_t)b * plane);
+        const uintptr_t nz_end = reinterpret_cast<uintptr_t>(p.noise + (size_t)p.B * plane);
         auto issue = [&](int c) {
             if (c >= n_chunks) return;
             const uint32_t g = g0 + (uint32_t)c;
@@ -449,10 +451,23 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int rows_h = h == 0 ? min(rows, R / 2) : max(rows - R / 2, 0);
-                const uint32_t bytes = (uint32_t)rows_h * ld * 4;
+                // the half's rows are rows_h * S consecutive floats of the draw; bulk copies move 16-byte units, so
+                // copy the aligned superset (the appliers skip the `mis` leading bytes) and finish a tail that would
+                // run past the end of the tensor by hand
+                const uintptr_t addr = nz_b + ((size_t)c * R + (size_t)h * (R / 2)) * p.S * 4;
+                const uint32_t mis = (uint32_t)(addr & 15);
+                const uintptr_t src0 = addr - mis;
+                const uint32_t want = rows_h ? mis + (uint32_t)rows_h * p.S * 4 : 0u;
+                uint32_t bulk = (want + 15u) & ~15u;
+                unsigned char *dst = smem + p.off_nz + h * half_stride;
                 mbar_wait(&nfree[h], (g & 1u) ^ 1u);              // every applier warp has read the previous contents
-                mbar_arrive_expect_tx(&nfull[h], bytes);          // (an empty half still completes its phase)
-                if (bytes) bulk_g2s(smem + p.off_nz + h * half_bytes, nz_b + ((size_t)c * R + (size_t)h * (R / 2)) * ld * 4, bytes, &nfull[h]);
+                if (src0 + bulk > nz_end) {
+                    bulk = want & ~15u;
+                    for (uint32_t o = bulk; o < want; o += 4)
+                        *reinterpret_cast<float *>(dst + o) = *reinterpret_cast<const float *>(src0 + o);
+                }
+                mbar_arrive_expect_tx(&nfull[h], bulk);           // (an empty half still completes its phase)
+                if (bulk) bulk_g2s(dst, reinterpret_cast<const void *>(src0), bulk, &nfull[h]);
             }
         };
         if (lane == 0) issue(0);
@@ -504,25 +519,42 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
             for (int h = 0; h < 2; ++h) {
                 const int rows_h = h == 0 ? min(rows, R / 2) : max(rows - R / 2, 0);
                 const int n4 = rows_h * ld4;
-                const float4 *nz4 = reinterpret_cast<const float4 *>(smem + p.off_nz + h * half_bytes) + gl;
+                const unsigned char *nzh = smem + p.off_nz + h * half_stride;
                 float4 *t4 = tile4 + (size_t)h * (R / 2) * ld4;
                 mbar_wait(&nfull[h], npar);
                 const long long h2 = MAS_TR(p) ? clock64() : 0;
-                float4 cv[KQ], nv[KQ];
+                if (nvec) {
+                    const float4 *nz4 = reinterpret_cast<const float4 *>(nzh) + gl;
+                    float4 cv[KQ], nv[KQ];
 #pragma unroll
-                for (int k = 0; k < KQ; ++k)
-                    if (gl + k * HT < n4) cv[k] = t4[k * HT], nv[k] = nz4[k * HT];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&nfree[h]);   // this warp has read the half: the next chunk's may come
+                    for (int k = 0; k < KQ; ++k)
+                        if (gl + k * HT < n4) cv[k] = t4[k * HT], nv[k] = nz4[k * HT];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&nfree[h]);   // this warp has read the half: the next chunk's may come
 #pragma unroll
-                for (int k = 0; k < KQ; ++k)
-                    if (gl + k * HT < n4) {
-                        cv[k].x = __fadd_rn(cv[k].x, __fmul_rn(__fmul_rn(sd, nv[k].x), scale));
-                        cv[k].y = __fadd_rn(cv[k].y, __fmul_rn(__fmul_rn(sd, nv[k].y), scale));
-                        cv[k].z = __fadd_rn(cv[k].z, __fmul_rn(__fmul_rn(sd, nv[k].z), scale));
-                        cv[k].w = __fadd_rn(cv[k].w, __fmul_rn(__fmul_rn(sd, nv[k].w), scale));
-                        t4[k * HT] = cv[k];
-                    }
+                    for (int k = 0; k < KQ; ++k)
+                        if (gl + k * HT < n4) {
+                            cv[k].x = __fadd_rn(cv[k].x, __fmul_rn(__fmul_rn(sd, nv[k].x), scale));
+                            cv[k].y = __fadd_rn(cv[k].y, __fmul_rn(__fmul_rn(sd, nv[k].y), scale));
+                            cv[k].z = __fadd_rn(cv[k].z, __fmul_rn(__fmul_rn(sd, nv[k].z), scale));
+                            cv[k].w = __fadd_rn(cv[k].w, __fmul_rn(__fmul_rn(sd, nv[k].w), scale));
+                            t4[k * HT] = cv[k];
+                        }
+                } else {
+                    // rows that are not a multiple of 16 bytes (real collated batches: data_utils.py:151-214): the
+                    // draw is packed with stride S, the private cost plane has stride ld; one element at a time
+                    const uintptr_t addr = reinterpret_cast<uintptr_t>(p.noise + (size_t)b * plane) +
+                                           ((size_t)c * R + (size_t)h * (R / 2)) * p.S * 4;
+                    const float *nzf = reinterpret_cast<const float *>(nzh + (addr & 15));
+                    float *tf = reinterpret_cast<float *>(t4 - gl);
+                    for (int r = 0; r < rows_h; ++r)
+                        for (int x = gl; x < p.S; x += HT) {
+                            float *q = tf + r * ld + x;
+                            *q = __fadd_rn(*q, __fmul_rn(__fmul_rn(sd, nzf[r * p.S + x]), scale));
+                        }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&nfree[h]);
+                }
                 if (MAS_TR(p)) {
                     const long long h3 = clock64();
                     hacc[1] += h2 - h1, hacc[2] += h3 - h2, h1 = h3;
@@ -545,12 +577,14 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
 // continue across utterances).
 // kHelp > 0: that many helper warps sit behind the producer warp and add VITS2's noise to every cost tile one chunk
 // step ahead of the value warps (dp_noise_helper).
-// Not inlined on purpose: the fused kernels run this after the contraction role, whose epilogue sits at the
-// 128-register limit of a 512-thread CTA; compiled into the same function, the value warps' loop inherited that
-// pressure (thread-index values rematerialised inside the row loop) and ran 60 % slower than in the standalone
-// DP kernel.
+// (Inlined: as a separate function -- tried so that the 128-register limit of the fused kernels' 512-thread CTAs
+// would not shape the value warps' loop -- the standalone kernel went from 43 to 59 us at config 2.
+// Also tried and dropped: point-to-point progress counters in shared memory instead of the CTA-wide barrier after
+// every chunk step (a warp polling only the neighbour it depends on).  All parity tests passed, but the two
+// MEMBAR.CTA per chunk and warp cost more than the barrier's wait: maximum_path 43 -> 47 us at config 2 and
+// 362 -> 474 us at config 4, where the chunks are 8-16 rows.)
 template <int C, int R, int W, bool kVec, bool kNoise = false, bool kVK = false, int kHelp = 0>
-__device__ __noinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
+__device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
                                         int bar)
 {
     const int warp = tid >> 5;

@@ -61,23 +61,25 @@ __global__ void __launch_bounds__(kGatherThreads) mas_gather_prior_kernel(const 
 // backward of the gather: g_in[b, d, s] = sum over the frames aligned to column s of g_out[b, d, t].
 // The path is monotonic, so those frames are the contiguous range [start_s, start_s + dur_s) with start = the
 // exclusive prefix sum of the durations: a segmented sum in a fixed (ascending t) order, no atomics.
-// One CTA = one utterance x kScatterD channels; a thread owns a text column and reads ITS segment of every
-// channel row straight from global memory: the segments of neighbouring columns are neighbouring frames, so a
-// warp's loads fall into a window of a few cache lines that the following iterations finish off out of L1, and
-// every gradient element is fetched from DRAM once.  kScatterD rows of both gradients give a thread 2 kScatterD
-// independent loads per frame to hide the latency behind.  (The first version staged 1024-frame tiles in shared
-// memory with CTA barriers around every tile: instruction- and barrier-bound, 93 us = 0.2 of the HBM roofline at
-// config 2.)
+// One CTA = one utterance x kScatterD channels.  The gradient rows stream through shared memory in chunks of
+// kScatterChunk frames with coalesced 16-byte loads; a thread then owns a text column (up to 4 for S = 1024)
+// and adds up the part of its segment that lies in the chunk.
+// (Tried in round 2 and dropped: no shared tile at all -- a thread reading its own segment of 8 + 8 channel rows
+// straight from global memory, neighbouring columns being neighbouring frames.  Every element comes from DRAM
+// once, but the scalar loads of a warp straddle 4-5 lines each and the kernel ran 328 us against 93 us here.)
 constexpr int kScatterThreads = 256;
-constexpr int kScatterD = 8;
+constexpr int kScatterD = 4;
+constexpr int kScatterChunk = 1024;   // frames per tile row = one 16-byte load per thread
 
-template <bool kTwo>
+template <bool kTwo, int kScatterCols>   // kScatterCols = ceil(S / 256) text columns per thread
 __global__ void __launch_bounds__(kScatterThreads) mas_scatter_prior_kernel(const float *__restrict__ g_m,
                                                                             const float *__restrict__ g_logs,
                                                                             const int32_t *__restrict__ dur,
                                                                             float *__restrict__ g_m_p,
                                                                             float *__restrict__ g_logs_p, int D, int T, int S)
 {
+    constexpr int kRows = kTwo ? 2 * kScatterD : kScatterD;
+    __shared__ __align__(16) float tile[kRows][kScatterChunk];
     __shared__ int start_s[MAS_MAX_TEXT + 1];
     __shared__ int warp_tot[kScatterThreads / 32];
     const int b = blockIdx.y, d0 = blockIdx.x * kScatterD, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -109,46 +111,60 @@ __global__ void __launch_bounds__(kScatterThreads) mas_scatter_prior_kernel(cons
     if (tid == kScatterThreads - 1) start_s[S] = run;
     __syncthreads();
 
-    // channel rows of this CTA (rows past D repeat the last one and are not stored)
-    const float *rm[kScatterD], *rl[kScatterD];
+    // row r of the tile: channel d0 + (r % kScatterD) of g_m (r < kScatterD) or g_logs
+    const float *rows[kRows];
 #pragma unroll
-    for (int r = 0; r < kScatterD; ++r) {
-        const size_t row = ((size_t)b * D + min(d0 + r, D - 1)) * T;
-        rm[r] = g_m + row;
-        rl[r] = kTwo ? g_logs + row : nullptr;
+    for (int r = 0; r < kRows; ++r) {
+        const int d = min(d0 + (r % kScatterD), D - 1);
+        rows[r] = ((kTwo && r >= kScatterD) ? g_logs : g_m) + ((size_t)b * D + d) * T;
     }
-    for (int s = tid; s < S; s += kScatterThreads) {
-        const int lo = min(start_s[s], T), hi = min(start_s[s + 1], T);
-        float am[kScatterD], al[kScatterD];
+    const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_m) & 15) == 0) &&
+                     (!kTwo || (reinterpret_cast<uintptr_t>(g_logs) & 15) == 0);
+    float acc[kScatterCols][kRows];
+    int lo[kScatterCols], hi[kScatterCols];
 #pragma unroll
-        for (int r = 0; r < kScatterD; ++r) am[r] = 0.0f, al[r] = 0.0f;
-        int t = lo;
-        for (; t + 2 <= hi; t += 2) {   // two frames per trip: 2 (4) kScatterD loads in flight
-            float vm[2][kScatterD], vl[2][kScatterD];
+    for (int c = 0; c < kScatterCols; ++c) {
+        const int s = tid + c * kScatterThreads;
+        lo[c] = s < S ? min(start_s[s], T) : 0;
+        hi[c] = s < S ? min(start_s[s + 1], T) : 0;
 #pragma unroll
-            for (int r = 0; r < kScatterD; ++r) {
-                vm[0][r] = __ldg(rm[r] + t), vm[1][r] = __ldg(rm[r] + t + 1);
-                if (kTwo) vl[0][r] = __ldg(rl[r] + t), vl[1][r] = __ldg(rl[r] + t + 1);
+        for (int r = 0; r < kRows; ++r) acc[c][r] = 0.0f;
+    }
+    for (int c0 = 0; c0 < T; c0 += kScatterChunk) {
+        const int n = min(kScatterChunk, T - c0);
+        if (vec) {
+            for (int i = tid * 4; i < n; i += kScatterThreads * 4) {
+#pragma unroll
+                for (int r = 0; r < kRows; ++r)
+                    *reinterpret_cast<float4 *>(&tile[r][i]) = __ldg(reinterpret_cast<const float4 *>(rows[r] + c0 + i));
             }
+        } else {
+            for (int i = tid; i < n; i += kScatterThreads) {
 #pragma unroll
-            for (int r = 0; r < kScatterD; ++r) {
-                am[r] = (am[r] + vm[0][r]) + vm[1][r];
-                if (kTwo) al[r] = (al[r] + vl[0][r]) + vl[1][r];
+                for (int r = 0; r < kRows; ++r) tile[r][i] = __ldg(rows[r] + c0 + i);
             }
         }
-        if (t < hi) {
+        __syncthreads();
 #pragma unroll
-            for (int r = 0; r < kScatterD; ++r) {
-                am[r] += __ldg(rm[r] + t);
-                if (kTwo) al[r] += __ldg(rl[r] + t);
+        for (int c = 0; c < kScatterCols; ++c) {
+            const int a = max(lo[c], c0) - c0, e = min(hi[c], c0 + n) - c0;
+            for (int t = a; t < e; ++t) {
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) acc[c][r] += tile[r][t];
             }
         }
+        __syncthreads();
+    }
 #pragma unroll
-        for (int r = 0; r < kScatterD; ++r) {
-            if (d0 + r >= D) continue;
-            const size_t o = ((size_t)b * D + d0 + r) * S + s;
-            g_m_p[o] = am[r];
-            if (kTwo) g_logs_p[o] = al[r];
+    for (int c = 0; c < kScatterCols; ++c) {
+        const int s = tid + c * kScatterThreads;
+        if (s >= S) continue;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int d = d0 + (r % kScatterD);
+            if (d >= D) continue;
+            float *dst = (kTwo && r >= kScatterD) ? g_logs_p : g_m_p;
+            dst[((size_t)b * D + d) * S + s] = acc[c][r];
         }
     }
 }
@@ -261,10 +277,19 @@ int expand_prior_backward_launch(const float *g_m, const float *g_logs, const in
                                  int B, int D, int T, int S, cudaStream_t stream)
 {
     const dim3 grid((unsigned)((D + kScatterD - 1) / kScatterD), (unsigned)B);
-    if (g_logs)
-        mas_scatter_prior_kernel<true><<<grid, kScatterThreads, 0, stream>>>(g_m, g_logs, dur, g_m_p, g_logs_p, D, T, S);
-    else
-        mas_scatter_prior_kernel<false><<<grid, kScatterThreads, 0, stream>>>(g_m, g_logs, dur, g_m_p, g_logs_p, D, T, S);
+#define MAS_SCATTER(TWO, COLS) \
+    mas_scatter_prior_kernel<TWO, COLS><<<grid, kScatterThreads, 0, stream>>>(g_m, g_logs, dur, g_m_p, g_logs_p, D, T, S)
+    const int cols = (S + kScatterThreads - 1) / kScatterThreads;
+    if (g_logs) {
+        if (cols <= 1) MAS_SCATTER(true, 1);
+        else if (cols == 2) MAS_SCATTER(true, 2);
+        else MAS_SCATTER(true, 4);
+    } else {
+        if (cols <= 1) MAS_SCATTER(false, 1);
+        else if (cols == 2) MAS_SCATTER(false, 2);
+        else MAS_SCATTER(false, 4);
+    }
+#undef MAS_SCATTER
     note_launch();
     MAS_CUDA_TRY(cudaGetLastError());
     return MAS_OK;

@@ -161,8 +161,7 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     MAS_CUDA_TRY(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const Config &cf = config();
-    // the DP CTAs stream the noise draw with 16-byte bulk copies
-    if (noise && ((S & 3) != 0 || (reinterpret_cast<uintptr_t>(noise) & 15) != 0)) return kFusedFallback;
+    if (noise && (reinterpret_cast<uintptr_t>(noise) & 3) != 0) return kFusedFallback;
     const int m_tiles = (T + kBM - 1) / kBM;
     const int ld = padded_ld(S);
     const int n_flags = B * (m_tiles + 1) + 2;
