@@ -636,6 +636,10 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     fence_proxy_async();
                     __syncwarp();
+                    // (Tried in round 2: reading the block back and storing it with plain coalesced 16-byte stores so
+                    // that the tile flag need not wait for the tensor-store engine -- a tile takes 5-7 us from the end
+                    // of the epilogue to its publication.  The epilogue then took 6.5 us per unit instead of 3.5 and
+                    // held up the accumulators: 82 -> 93 us per step at config 2.)
                     if (lane == 0) {
                         tma_store_3d(tm_out, c_base + c0, mt * kBM + wq * 32, b, buf);  // rows >= T / cols >= S are clipped
                         bulk_commit();
