@@ -46,6 +46,10 @@ def _worker(rank, world, port, batch, S, T, out_dir):
         dur = torch.from_numpy(path.sum(1).astype(np.int32))
         g_idx, g_dur = sharded.gather_compact(idx, dur, batch)
         assert g_idx.shape == (batch, T) and g_dur.shape == (batch, S)
+        if batch % world == 0:
+            # fixed-shape buckets: the one-collective path gives the same result
+            u_idx, u_dur = sharded.gather_compact(idx, dur, batch, uniform=True)
+            assert torch.equal(u_idx, g_idx) and torch.equal(u_dur, g_dur)
         torch.save((g_idx, g_dur), os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()

@@ -48,6 +48,7 @@ struct Config {
     int fused_zero_offload;  // MAS_FUSED_ZERO_OFFLOAD=0: the DP CTAs zero-fill their own path planes
     int fused_pdl;       // MAS_FUSED_PDL=0: no programmatic dependent launch
     int noise_fused;     // MAS_NOISE_FUSED=0: noise-scaled alignment as separate launches
+    int noise_feed;      // MAS_NOISE_FEED=0: no {DP CTA, noise feeder CTA} pairs (helper warps inside the DP CTAs instead)
     int stage;           // MAS_STAGE: 1 = prior preparation only, 2 = skip it (reuse the images in the workspace);
                          // bench.py times the prior kernel alone with it
     int tc_debug, dp_debug, tc_no_tma, tc_grid, tc_pair, trace;   // trace build only (MAS_TC_DEBUG, MAS_DP_DEBUG, ...)
@@ -126,6 +127,59 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
             smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// ---- distributed shared memory (CTA pair of a cluster) ----------------------
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsm_map(uint32_t local, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsm_st_v4(uint32_t cluster_addr, float4 v)
+{
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+// asynchronous 16-byte store into another CTA's shared memory; its arrival is counted (16 bytes) on the mbarrier
+// `cluster_mbar` of that CTA, so the reader needs nothing but its usual wait on the barrier and the writer no fence
+__device__ __forceinline__ void dsm_st_async_v4(uint32_t cluster_addr, float4 v, uint32_t cluster_mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     cluster_addr),
+                 "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+                 "r"(cluster_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void dsm_st_u32(uint32_t cluster_addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster; orders this thread's earlier (remote) stores before it
+__device__ __forceinline__ void dsm_mbar_arrive_release(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local mbarrier that threads of another CTA of the cluster arrive on (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 
 // prefetch the 128-byte line holding `p` into L2

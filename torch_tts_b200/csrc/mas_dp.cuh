@@ -76,6 +76,11 @@ struct DpParams {
     int R;       // mel rows per chunk (template parameter of the role; 32, 16 or 8)
     int W;       // DP warps per team (template parameter of the role; 2 or 4)
     int vk;      // value / origin warp split (W value warps + W origin warps + producer)
+    int fed;     // > 0: the cost tiles are pushed into the stage ring by the partner CTA of the cluster (noise feeder,
+                 // mas_fused.cu) with asynchronous stores counted on the stage's full barrier; the producer warp only
+                 // arms the barriers with the tiles' byte counts and returns one credit per consumed stage
+    uint32_t fed_credit_off;   // byte offset of the feeder's credit barriers [kMaxStages] in ITS dynamic shared memory
+    uint32_t fed_verdict_off;  // ... of its {verdict barrier (8 bytes), verdict word}
     int help;    // noise-helper warps behind the producer warp (fused noise kernel): they add (std * noise) * scale to
                  // every cost tile in shared memory one chunk step ahead of the value warps
     int stages;  // cost-tile ring depth (2..kMaxStages)
@@ -583,7 +588,8 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
 // every chunk step (a warp polling only the neighbour it depends on).  All parity tests passed, but the two
 // MEMBAR.CTA per chunk and warp cost more than the barrier's wait: maximum_path 43 -> 47 us at config 2 and
 // 362 -> 474 us at config 4, where the chunks are 8-16 rows.)
-template <int C, int R, int W, bool kVec, bool kNoise = false, bool kVK = false, int kHelp = 0>
+// kFed: the cost tiles arrive from the partner CTA (see DpParams::fed).
+template <int C, int R, int W, bool kVec, bool kNoise = false, bool kVK = false, int kHelp = 0, bool kFed = false>
 __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, int b, int slot, uint32_t &g_base, int tid,
                                         int bar)
 {
@@ -595,6 +601,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     constexpr int S_bits = S_pad + kBitsPad;
     static_assert(!kVK || R == kCheck, "the warp split replays whole decision words: one chunk = one word");
     static_assert(kHelp == 0 || (kVec && !kNoise), "helper warps work on 16-byte rows and replace the in-loop noise");
+    static_assert(!kFed || (kVec && !kNoise && kHelp == 0), "the feeder delivers finished (noised) tiles with 16-byte rows");
     constexpr int kThreads = dp_threads(W, kVK) + 32 * kHelp;
     constexpr int kDpWarps = W;                       // warps that consume cost tiles
     constexpr int kProducerWarp = kVK ? 2 * W : W;
@@ -730,9 +737,19 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     if (bulk) bulk_g2s(dst, src, bulk, &full[st]);
                 }
             };
+            // kFed: the partner CTA writes the tiles; arm the stage's barrier with the bytes it is going to send
+            auto arm_tile = [&](int c) {
+                const uint32_t st_a = (g0 + (uint32_t)c) % n_stages;
+                mbar_arrive_expect_tx(&full[st_a], (uint32_t)min(R, t_y - c * R) * ld * 4);
+            };
             if (lane == 0) {
                 const int pre = min((int)n_stages, n_chunks);
-                for (int c = 0; c < pre; ++c) issue_tile(c);
+                for (int c = 0; c < pre; ++c) {
+                    if (kFed)
+                        arm_tile(c);
+                    else
+                        issue_tile(c);
+                }
             }
             // zero-fill of the dense path, spread over the chunk steps: TMA bulk stores from a
             // zeroed shared buffer when the plane is 16-byte aligned, plain stores otherwise
@@ -760,7 +777,17 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                 bar_sync(bar, kThreads);
                 const long long q2 = MAS_TR(p) ? clock64() : 0;
                 const int freed = step - (kDpWarps - 1) - kHs;
-                if (lane == 0 && freed >= 0 && freed + (int)n_stages < n_chunks) issue_tile(freed + (int)n_stages);
+                if (kFed) {
+                    // the stage of chunk `freed` has been read by every value warp: hand it back to the feeder (one
+                    // credit per chunk, so that its phase count stays in step with the running tile number)
+                    if (lane == 0 && freed >= 0 && freed < n_chunks) {
+                        const uint32_t st_f = (g0 + (uint32_t)freed) % n_stages;
+                        if (freed + (int)n_stages < n_chunks) arm_tile(freed + (int)n_stages);   // before the credit
+                        dsm_mbar_arrive_release(dsm_map(smem_u32(smem + p.fed_credit_off + st_f * 8), 1u));
+                    }
+                } else if (lane == 0 && freed >= 0 && freed + (int)n_stages < n_chunks) {
+                    issue_tile(freed + (int)n_stages);
+                }
                 __syncwarp();
                 if (MAS_TR(p)) {
                     const long long q3 = clock64();
@@ -866,7 +893,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                     const uint32_t mis = kVec ? 0u : (uint32_t)(((utt_elem0 + (size_t)row0 * ld) * 4) & 15);
                     const float *tile =
                         reinterpret_cast<const float *>(smem + p.off_stage + (size_t)st * p.stage_bytes + mis);
-                    mbar_wait(&full[st], st_par);
+                    mbar_wait(&full[st], st_par);   // (kFed: the partner CTA's asynchronous stores complete the phase)
                     if (MAS_TR(p)) d1 = clock64();
                     const bool edge = row0 < edge_rows;
 #define MAS_CHUNK(EDGE, EXACT)                                                                             \
@@ -949,7 +976,13 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
         if (saw_nonfinite) *nonfinite_s = 1;
         bar_sync(bar, kThreads);
         passes = pass + 1;
-        if (pass == 1 || *nonfinite_s == 0) break;
+        const bool again = (pass == 0 && *nonfinite_s != 0);
+        if (kFed && tid == 0) {
+            // tell the feeder whether the tiles have to be streamed once more (exact pass)
+            dsm_st_u32(dsm_map(smem_u32(smem + p.fed_verdict_off + 8), 1u), again ? 1u : 0u);
+            dsm_mbar_arrive_release(dsm_map(smem_u32(smem + p.fed_verdict_off), 1u));
+        }
+        if (!again) break;
     }
     g_base += (uint32_t)passes * n_chunks;
     if (!p.bits_in_smem || !p.hop_in_smem) __threadfence_block();

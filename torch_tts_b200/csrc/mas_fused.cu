@@ -33,6 +33,10 @@ struct FusedParams {
     DpParams dp;
     int n_dp;              // the first n_dp CTAs turn into DP CTAs after their share of the contraction
     uint32_t *grid_bar;    // noise kernel: grid barrier counter (cleared with the flags)
+    int feed_pairs;        // noise kernel: > 0 = that many CTA pairs run {DP CTA, noise feeder CTA} after the barrier
+    const float *noise;    // noise kernel with feeders: the draw [B][T][S] (16-byte rows), its scale, the statistics
+    float noise_scale;
+    const double *stats;
 };
 
 constexpr int kNoiseHelpWarps = 8;   // helper warps of a DP CTA in the noise kernel (dp_role, kHelp)
@@ -93,8 +97,167 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_c
 #endif
 
 // ---------------------------------------------------------------------------
-// noise-scaled alignment: contraction + statistics | grid barrier | DP (noise applied by helper warps) + zero fill
+// noise-scaled alignment: contraction + statistics | grid barrier | DP + noise
 // ---------------------------------------------------------------------------
+// Noise feeder (batches of at most one utterance per CTA pair, the VITS2 default of 64 per GPU included): after the
+// grid barrier the even CTA of a pair runs the PLAIN DP role and the odd CTA -- idle otherwise -- feeds it: it
+// streams the cost tile (out of L2) and the same cells of the draw (out of HBM) through its own bulk-copy engine
+// into its own shared memory, adds (std * noise) * scale with all its warps and writes the finished tile straight
+// into the DP CTA's stage ring through distributed shared memory, then arrives on that stage's mbarrier.  The DP
+// CTA's shared-memory bandwidth, issue slots and bulk-copy engine carry nothing but the DP (with the helper warps
+// inside the DP CTA a 32-row step took 3400 cycles instead of 2170); its producer warp only returns one credit per
+// consumed stage.  The feeder also zero-fills its partner's path plane.
+constexpr int kFeedStages = 3;                 // feeder ring: {cost tile, noise tile} per stage
+constexpr int kFeedWarps = 15;                 // applier warps (warp 15 issues the bulk copies)
+constexpr int kFeedAhead = 6;                  // chunks of the draw kept ahead in L2
+constexpr uint32_t kFeedOffEmpty = 32, kFeedOffCredit = 64, kFeedOffVerdict = 128, kFeedOffZero = 256;
+constexpr uint32_t kFeedZeroBytes = 16384;
+constexpr uint32_t kFeedOffStage = kFeedOffZero + kFeedZeroBytes;
+__host__ __device__ inline uint32_t feed_tile_bytes(int R, int ld) { return (uint32_t)(((size_t)R * ld * 4 + 127) & ~(size_t)127); }
+__host__ __device__ inline uint32_t feed_smem_bytes(int R, int ld) { return kFeedOffStage + kFeedStages * 2 * feed_tile_bytes(R, ld); }
+
+__device__ __forceinline__ void noise_feeder_init(unsigned char *smem)
+{
+    uint64_t *ffull = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *fempty = reinterpret_cast<uint64_t *>(smem + kFeedOffEmpty);
+    uint64_t *credit = reinterpret_cast<uint64_t *>(smem + kFeedOffCredit);
+    uint64_t *verdict = reinterpret_cast<uint64_t *>(smem + kFeedOffVerdict);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kFeedStages; ++i) {
+            mbar_init(&ffull[i], 1);
+            mbar_init(&fempty[i], kFeedWarps);
+        }
+        for (int i = 0; i < kMaxStages; ++i) mbar_init(&credit[i], 1);
+        mbar_init(verdict, 1);
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < (int)(kFeedZeroBytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(smem + kFeedOffZero)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();   // the zero page is read by the bulk-store engine
+}
+
+template <int R>
+__device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigned char *smem, int first, int stride)
+{
+    const DpParams &p = fp.dp;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int HT = kFeedWarps * 32;
+    uint64_t *ffull = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *fempty = reinterpret_cast<uint64_t *>(smem + kFeedOffEmpty);
+    uint64_t *credit = reinterpret_cast<uint64_t *>(smem + kFeedOffCredit);
+    uint64_t *verdict = reinterpret_cast<uint64_t *>(smem + kFeedOffVerdict);
+    volatile uint32_t *verdict_val = reinterpret_cast<volatile uint32_t *>(smem + kFeedOffVerdict + 8);
+    const int T = p.T, S = p.S, ld = p.ld, ld4 = ld >> 2;     // (ld == S: checked by the launcher)
+    const size_t plane = (size_t)T * S;
+    const uint32_t tile_bytes = feed_tile_bytes(R, ld);
+    const uint32_t n_stages = (uint32_t)p.stages;
+    const int esize = path_elem_size(p.path_dtype);
+    // unbiased std over ALL cells, padding included (torch.std default, models.py:1243), from fp64 sums
+    float sd;
+    {
+        const double n = (double)p.B * (double)plane;
+        const double s0 = __ldcg(fp.stats), s1 = __ldcg(fp.stats + 1);
+        const double mean = s0 / n;
+        double var = (s1 - s0 * mean) / (n > 1.0 ? n - 1.0 : 1.0);
+        if (var < 0) var = 0;
+        sd = (float)sqrt(var);
+    }
+    const float scale = fp.noise_scale;
+    // the partner's stage ring and its full barriers, as shared::cluster addresses of cluster rank 0
+    const uint32_t r_stage0 = dsm_map(smem_u32(smem + p.off_stage), 0u);
+    const uint32_t r_full0 = dsm_map(smem_u32(smem + p.off_bar), 0u);
+    uint32_t g_base = 0, n_verdicts = 0;
+    for (int b = first; b < p.B; b += stride) {
+        const int t_y = p.t_ys[b], t_x = p.t_xs[b];
+        if (!(t_x >= 1 && t_x <= t_y && t_y <= T && t_x <= S)) continue;   // the DP role skips it the same way
+        const int n_chunks = (t_y + R - 1) / R;
+        const unsigned char *cost_b = reinterpret_cast<const unsigned char *>(p.neg_cent + (size_t)b * T * ld);
+        const unsigned char *nz_b = reinterpret_cast<const unsigned char *>(fp.noise + (size_t)b * plane);
+        int passes = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint32_t g0 = g_base + (uint32_t)pass * n_chunks;
+            if (warp == kFeedWarps) {
+                // ---- bulk-copy issuer: tile loads, and (first pass) the zero fill of the partner's path plane ----
+                if (lane == 0) {
+                    unsigned char *path_b = (pass == 0 && p.path) ? p.path + (size_t)b * plane * esize : nullptr;
+                    const size_t pbytes = path_b ? plane * esize : 0;
+                    const size_t quota = align_up((pbytes + n_chunks - 1) / n_chunks, kFeedZeroBytes);
+                    for (int c = 0; c < n_chunks; ++c) {
+                        const uint32_t g = g0 + (uint32_t)c, s = g % kFeedStages, u = g / kFeedStages;
+                        const uint32_t bytes = (uint32_t)min(R, t_y - c * R) * ld * 4;
+                        mbar_wait(&fempty[s], (u & 1u) ^ 1u);
+                        unsigned char *dst = smem + kFeedOffStage + s * 2 * tile_bytes;
+                        mbar_arrive_expect_tx(&ffull[s], 2 * bytes);
+                        bulk_g2s(dst, cost_b + (size_t)c * R * ld * 4, bytes, &ffull[s]);
+                        bulk_g2s(dst + tile_bytes, nz_b + (size_t)c * R * ld * 4, bytes, &ffull[s]);
+                        size_t lo = (size_t)c * quota, hi = lo + quota;
+                        if (lo > pbytes) lo = pbytes;
+                        if (hi > pbytes) hi = pbytes;
+                        if (hi > lo) {
+                            for (size_t o = lo; o < hi; o += kFeedZeroBytes)
+                                bulk_s2g(path_b + o, smem + kFeedOffZero, (uint32_t)min((size_t)kFeedZeroBytes, hi - o));
+                            bulk_commit();
+                        }
+                    }
+                    if (path_b) {
+                        // the DP CTA scatters the ones only after the zeros have landed
+                        bulk_wait_all();
+                        fence_proxy_async_all();
+                        __threadfence();
+                        atomicAdd(p.zero_flags + b, (uint32_t)kZeroParts);
+                    }
+                }
+                __syncwarp();
+            } else {
+                // ---- appliers: cost + (std * noise) * scale, rounded after every operation (models.py:1242-1247),
+                //      from this CTA's stage straight into the partner's ----
+                const int gl = warp * 32 + lane;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const uint32_t g = g0 + (uint32_t)c, s = g % kFeedStages, u = g / kFeedStages;
+                    const uint32_t st = g % n_stages, ud = g / n_stages;
+                    const int n4 = min(R, t_y - c * R) * ld4;
+                    const float4 *c4 = reinterpret_cast<const float4 *>(smem + kFeedOffStage + s * 2 * tile_bytes) + gl;
+                    const float4 *z4 = reinterpret_cast<const float4 *>(smem + kFeedOffStage + s * 2 * tile_bytes + tile_bytes) + gl;
+                    // the draw a few chunks ahead: into L2, one 128-byte line per thread
+                    if (c + kFeedAhead < n_chunks) {
+                        const int pbytes = min(R, t_y - (c + kFeedAhead) * R) * ld * 4;
+                        if (gl * 128 < pbytes) prefetch_l2(nz_b + (size_t)(c + kFeedAhead) * R * ld * 4 + gl * 128);
+                    }
+                    mbar_wait(&ffull[s], u & 1u);
+                    constexpr int KQ = (R * 64 + HT - 1) / HT;   // items per thread and chunk at the widest plane (256 floats)
+                    float4 cv[KQ], nv[KQ];
+#pragma unroll
+                    for (int k = 0; k < KQ; ++k)
+                        if (gl + k * HT < n4) cv[k] = c4[k * HT], nv[k] = z4[k * HT];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fempty[s]);            // this warp has read the stage
+                    mbar_wait_acq_cluster(&credit[st], (ud & 1u) ^ 1u);   // the partner has consumed the stage's previous tile
+                    const uint32_t dst = r_stage0 + st * p.stage_bytes + (uint32_t)gl * 16u;
+#pragma unroll
+                    for (int k = 0; k < KQ; ++k)
+                        if (gl + k * HT < n4) {
+                            cv[k].x = __fadd_rn(cv[k].x, __fmul_rn(__fmul_rn(sd, nv[k].x), scale));
+                            cv[k].y = __fadd_rn(cv[k].y, __fmul_rn(__fmul_rn(sd, nv[k].y), scale));
+                            cv[k].z = __fadd_rn(cv[k].z, __fmul_rn(__fmul_rn(sd, nv[k].z), scale));
+                            cv[k].w = __fadd_rn(cv[k].w, __fmul_rn(__fmul_rn(sd, nv[k].w), scale));
+                            // asynchronous store: counted on the partner's full barrier of the stage, which its
+                            // producer lane has armed with the tile's byte count (no fence, no arrive here: a
+                            // release-arrive per warp and tile cost the feeder 1.9 us per chunk)
+                            dsm_st_async_v4(dst + (uint32_t)(k * HT) * 16u, cv[k], r_full0 + st * 8u);
+                        }
+                }
+            }
+            // does the DP want the tiles once more (exact pass after a non-finite cost)?
+            mbar_wait_acq_cluster(verdict, n_verdicts & 1u);
+            const uint32_t again = *verdict_val;
+            ++n_verdicts;
+            passes = pass + 1;
+            if (!again) break;
+        }
+        g_base += (uint32_t)passes * n_chunks;
+    }
+}
+
 template <int C, int R, int W, bool kVK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     mas_fused_noise_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CUtensorMap tm_z,
@@ -105,6 +268,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + blockIdx.x] = globaltimer_ns();  // CTA entry
     cost_tc_role<true, true>(fp.tc, &tm_z, &tm_out, smem, blockIdx.x >> 1, gridDim.x >> 1);
     if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 256 + blockIdx.x] = globaltimer_ns();  // contraction done
+    // with feeders: both CTAs of a pair set their barriers up BEFORE the grid barrier, so that neither can arrive on
+    // a barrier of the other that does not exist yet
+    const bool in_pair = kVK && fp.feed_pairs > 0 && (int)blockIdx.x < 2 * fp.feed_pairs;
+    const bool is_feeder = in_pair && (blockIdx.x & 1u);
+    if (in_pair) {
+        if (is_feeder)
+            noise_feeder_init(smem);
+        else if ((int)threadIdx.x < dp_threads(W, kVK))
+            dp_role_init(fp.dp, smem, threadIdx.x, kDpBar);
+    }
     // grid barrier: every CTA's tiles are in memory (L2) and its partial sums are in stats[]
     fence_proxy_async_all();
     __threadfence();
@@ -118,13 +291,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     }
     __syncthreads();
     if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 512 + blockIdx.x] = globaltimer_ns();  // barrier passed
+    if (kVK && fp.feed_pairs > 0) {
+        if (!in_pair) return;
+        if (is_feeder) {
+            noise_feeder_role<R>(fp, smem, (int)(blockIdx.x >> 1), fp.feed_pairs);
+            if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 768 + blockIdx.x] = globaltimer_ns();  // feeder done
+            return;
+        }
+        if ((int)threadIdx.x >= dp_threads(W, kVK)) return;
+        uint32_t g_base = 0;
+        for (int b = (int)(blockIdx.x >> 1); b < fp.dp.B; b += fp.feed_pairs)
+            dp_role<C, R, W, true, false, kVK, 0, true>(fp.dp, smem, b, (int)(blockIdx.x >> 1), g_base, threadIdx.x, kDpBar);
+        return;
+    }
     if ((int)blockIdx.x >= fp.n_dp) {
         if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem);
         if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 1024 + blockIdx.x] = globaltimer_ns();  // zero fill done
         return;
     }
-    // phase 2: the DP; the helper warps of every DP CTA add (std * noise) * scale to its cost tiles in shared
-    // memory, so the value warps run the plain body and the draw is read exactly once
+    // phase 2 without feeders (more utterances than CTA pairs): the helper warps of every DP CTA add
+    // (std * noise) * scale to its cost tiles in shared memory; the draw is read exactly once
     fused_dp_ctas<C, R, W, kVK, kNoiseHelpWarps>(fp, smem);
 }
 
@@ -165,10 +351,15 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     const int m_tiles = (T + kBM - 1) / kBM;
     const int ld = padded_ld(S);
     const int n_flags = B * (m_tiles + 1) + 2;
+    // Noise: one utterance per CTA pair at most (and 16-byte rows of the draw) -> {DP CTA, noise feeder CTA} pairs;
+    // larger batches -> every CTA a DP CTA with its own noise-helper warps
+    const int grid_ctas = sms & ~1;
+    const bool feed = noise && cf.noise_feed && 2 * B <= grid_ctas && (S & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(noise) & 15) == 0;
     // the DP plan first: nothing has been launched yet if it turns out not to fit
     DpPlan dp;
     int rc = dp_prepare(dp, plane, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, dp_ws, dp_ws_bytes, B, T,
-                        S, nullptr, 0, 0, false, ld, noise ? kNoiseHelpWarps : 0);
+                        S, nullptr, 0, 0, false, ld, (noise && !feed) ? kNoiseHelpWarps : 0);
     if (rc) return noise ? kFusedFallback : rc;
     TcPlan tc;
     // mel tiles wholly past t_y are skipped (the plane is private scratch) unless the noise statistics need them
@@ -183,20 +374,19 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     const bool pair = noise ? true : cost_tc_pair_enabled();
     const int per = pair ? 2 : 1;
 
-#ifdef MAS_TRACE
-#define MAS_FUSED_KERNEL(CC, WW, VK)                                                                       \
-    (noise  ? (const void *)mas_fused_noise_kernel<CC, 32, WW, VK>                                         \
-     : pair ? (const void *)mas_fused_pair_kernel<CC, 32, WW, VK>                                          \
-            : (const void *)mas_fused_kernel<CC, 32, WW, VK>)
-#else
-#define MAS_FUSED_KERNEL(CC, WW, VK) \
-    (noise ? (const void *)mas_fused_noise_kernel<CC, 32, WW, VK> : (const void *)mas_fused_pair_kernel<CC, 32, WW, VK>)
-#endif
     // S <= 256 (one column block): C = ceil(S / 64) columns per thread with 2 DP warps, or 2 columns with 4
-    // (value / origin warp split unless MAS_DP_VK=0)
+    // (value / origin warp split unless MAS_DP_VK=0).  The noise kernel exists for the warp-split teams only.
     const void *kernel = nullptr;
+#ifdef MAS_TRACE
+#define MAS_FUSED_PLAIN(CC, WW, VK) \
+    (pair ? (const void *)mas_fused_pair_kernel<CC, 32, WW, VK> : (const void *)mas_fused_kernel<CC, 32, WW, VK>)
+#else
+#define MAS_FUSED_PLAIN(CC, WW, VK) ((const void *)mas_fused_pair_kernel<CC, 32, WW, VK>)
+#endif
 #define MAS_FUSED_CASE(CC, WW, VK) \
-    if (dp.C == CC && dp.p.R == 32 && dp.p.W == WW && (dp.p.vk != 0) == VK) kernel = MAS_FUSED_KERNEL(CC, WW, VK);
+    if (!noise && dp.C == CC && dp.p.R == 32 && dp.p.W == WW && (dp.p.vk != 0) == VK) kernel = MAS_FUSED_PLAIN(CC, WW, VK);
+#define MAS_NOISE_CASE(CC) \
+    if (noise && dp.C == CC && dp.p.R == 32 && dp.p.W == 2 && dp.p.vk) kernel = (const void *)mas_fused_noise_kernel<CC, 32, 2, true>;
     MAS_FUSED_CASE(1, 2, true)
     MAS_FUSED_CASE(2, 2, true)
     MAS_FUSED_CASE(3, 2, true)
@@ -206,13 +396,20 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     MAS_FUSED_CASE(2, 2, false)
     MAS_FUSED_CASE(3, 2, false)
     MAS_FUSED_CASE(4, 2, false)
+    MAS_NOISE_CASE(1)
+    MAS_NOISE_CASE(2)
+    MAS_NOISE_CASE(3)
+    MAS_NOISE_CASE(4)
 #undef MAS_FUSED_CASE
-#undef MAS_FUSED_KERNEL
+#undef MAS_NOISE_CASE
+#undef MAS_FUSED_PLAIN
     if (!kernel) return kFusedFallback;
 
     size_t smem = dp.smem_bytes;
     if (smem < kTcSmem) smem = kTcSmem;
     if (smem < kZeroFillBuf) smem = kZeroFillBuf;
+    if (feed && smem < feed_smem_bytes(dp.p.R, ld)) smem = feed_smem_bytes(dp.p.R, ld);
+    if (smem > (size_t)kSmemBudget) return kFusedFallback;
     // all CTAs must be co-resident (the DP CTAs spin on flags the others raise): check what this context can
     // actually hold, one CTA per SM at most
     MAS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -277,17 +474,29 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     fp.tc.flags = noise ? nullptr : flags;    // noise: the whole plane exists before the first DP row (grid barrier)
     fp.dp.flags = noise ? nullptr : flags;
     if (noise) {
-        if (!dp.p.vk) return kFusedFallback;   // the helper warps come with the value / origin split
+        if (!dp.p.vk) return kFusedFallback;   // the helper warps / the feeder come with the value / origin split
         fp.dp.noise = noise;
         fp.dp.stats = stats;
         fp.dp.noise_scale = noise_scale;
-        fp.dp.help = kNoiseHelpWarps;
+        fp.noise = noise;
+        fp.stats = stats;
+        fp.noise_scale = noise_scale;
+        if (feed) {
+            fp.feed_pairs = B;
+            fp.dp.help = 0;
+            fp.dp.fed = 1;
+            fp.dp.fed_credit_off = kFeedOffCredit;
+            fp.dp.fed_verdict_off = kFeedOffVerdict;
+        } else {
+            fp.dp.help = kNoiseHelpWarps;
+        }
     }
     fp.tc.trace = trace_buffer();
     fp.dp.trace = fp.tc.trace;
     fp.dp.flag_tiles = m_tiles;
     // the contraction-only CTAs zero-fill the path planes when there are enough of them to do it in time
-    const bool offload = path_out && cf.fused_zero_offload && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1;
+    // (with feeders: the feeder CTA of the pair zero-fills its partner's plane)
+    const bool offload = path_out && (feed || (cf.fused_zero_offload && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1));
     fp.dp.zero_flags = offload ? flags + (size_t)B * m_tiles : nullptr;
     fp.dp.zero_queue = flags + (size_t)B * (m_tiles + 1);
     fp.grid_bar = flags + (size_t)B * (m_tiles + 1) + 1;

@@ -19,17 +19,27 @@ def shard_bounds(batch: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_compact(idx: torch.Tensor, dur: torch.Tensor, batch=None, group=None):
+def gather_compact(idx: torch.Tensor, dur: torch.Tensor, batch=None, group=None, uniform: bool = False):
     """All-gather per-rank compact results into global [batch, T_max] / [batch, S_max].
 
     Ranks may hold different numbers of utterances AND different padded sizes: under DDP every rank's batch is
     padded by TextAudioCollate to its own longest text / spectrogram (data_utils.py:168-177), so T and S differ
     from rank to rank.  The ranks first agree on (shard size, T, S) maxima with one small all-gather, then every
     rank pads to them (idx with -1 = "no frame", durations with 0) for the one data collective.
-    `batch`, when given, is checked against the gathered total."""
+    `batch`, when given, is checked against the gathered total.
+    uniform=True: the caller guarantees that every rank holds the same number of utterances with the same padded T and
+    S (fixed-shape buckets): no size exchange and no host synchronisation, one collective on the packed
+    [n, T + S] int32 block."""
     world = dist.get_world_size(group)
     n, T = idx.shape
     S = dur.shape[1]
+    if uniform:
+        packed = torch.cat([idx, dur], 1)
+        out = torch.empty((world * n, T + S), dtype=torch.int32, device=idx.device)
+        dist.all_gather_into_tensor(out, packed, group=group)
+        if batch is not None and out.shape[0] != batch:
+            raise _lib.MasError(f"gather_compact: ranks hold {out.shape[0]} utterances in total, caller expected {batch}")
+        return out[:, :T].contiguous(), out[:, T:].contiguous()
     mine = torch.tensor([n, T, S], dtype=torch.int64, device=idx.device)
     sizes = torch.empty((world * 3,), dtype=torch.int64, device=idx.device)
     dist.all_gather_into_tensor(sizes, mine, group=group)
