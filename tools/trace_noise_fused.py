@@ -53,7 +53,7 @@ tr = buf[40960:40960 + B * 16].reshape(B, 16).astype(np.int64)
 n_steps = (T + 31) // 32 + 4
 for name, off, labels in [("value warp 0", 0, ["tile wait", "compute", "bits/hop", "barrier"]),
                           ("producer", 8, ["zero-fill issue", "barrier", "tile issue"]),
-                          ("helper thread 0", 12, ["noise half wait", "apply"]),
+                          ("helper / feeder thread 0", 12, ["wait (loads)", "read", "wait (credit)", "apply + store"]),
                           ("issue_tile", 0, None)]:
     if labels is None:
         for lab, slot in (("flag/pad/fence", 11), ("arrive.expect_tx", 14), ("bulk issue", 15)):

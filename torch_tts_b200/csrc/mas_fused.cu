@@ -106,13 +106,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mas_fused_kernel(const __grid_c
 // into the DP CTA's stage ring through distributed shared memory, then arrives on that stage's mbarrier.  The DP
 // CTA's shared-memory bandwidth, issue slots and bulk-copy engine carry nothing but the DP (with the helper warps
 // inside the DP CTA a 32-row step took 3400 cycles instead of 2170); its producer warp only returns one credit per
-// consumed stage.  The feeder also zero-fills its partner's path plane.
+// consumed stage (and, its bulk-copy engine being free, zero-fills its own path plane as it goes).
 constexpr int kFeedStages = 3;                 // feeder ring: {cost tile, noise tile} per stage
 constexpr int kFeedWarps = 15;                 // applier warps (warp 15 issues the bulk copies)
 constexpr int kFeedAhead = 6;                  // chunks of the draw kept ahead in L2
-constexpr uint32_t kFeedOffEmpty = 32, kFeedOffCredit = 64, kFeedOffVerdict = 128, kFeedOffZero = 256;
-constexpr uint32_t kFeedZeroBytes = 16384;
-constexpr uint32_t kFeedOffStage = kFeedOffZero + kFeedZeroBytes;
+constexpr uint32_t kFeedOffEmpty = 32, kFeedOffCredit = 64, kFeedOffVerdict = 128, kFeedOffStage = 256;
 __host__ __device__ inline uint32_t feed_tile_bytes(int R, int ld) { return (uint32_t)(((size_t)R * ld * 4 + 127) & ~(size_t)127); }
 __host__ __device__ inline uint32_t feed_smem_bytes(int R, int ld) { return kFeedOffStage + kFeedStages * 2 * feed_tile_bytes(R, ld); }
 
@@ -131,9 +129,6 @@ __device__ __forceinline__ void noise_feeder_init(unsigned char *smem)
         mbar_init(verdict, 1);
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < (int)(kFeedZeroBytes / 16); i += blockDim.x)
-        reinterpret_cast<uint4 *>(smem + kFeedOffZero)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async();   // the zero page is read by the bulk-store engine
 }
 
 template <int R>
@@ -151,7 +146,6 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
     const size_t plane = (size_t)T * S;
     const uint32_t tile_bytes = feed_tile_bytes(R, ld);
     const uint32_t n_stages = (uint32_t)p.stages;
-    const int esize = path_elem_size(p.path_dtype);
     // unbiased std over ALL cells, padding included (torch.std default, models.py:1243), from fp64 sums
     float sd;
     {
@@ -177,11 +171,8 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
         for (int pass = 0; pass < 2; ++pass) {
             const uint32_t g0 = g_base + (uint32_t)pass * n_chunks;
             if (warp == kFeedWarps) {
-                // ---- bulk-copy issuer: tile loads, and (first pass) the zero fill of the partner's path plane ----
+                // ---- bulk-copy issuer: the tile loads ----
                 if (lane == 0) {
-                    unsigned char *path_b = (pass == 0 && p.path) ? p.path + (size_t)b * plane * esize : nullptr;
-                    const size_t pbytes = path_b ? plane * esize : 0;
-                    const size_t quota = align_up((pbytes + n_chunks - 1) / n_chunks, kFeedZeroBytes);
                     for (int c = 0; c < n_chunks; ++c) {
                         const uint32_t g = g0 + (uint32_t)c, s = g % kFeedStages, u = g / kFeedStages;
                         const uint32_t bytes = (uint32_t)min(R, t_y - c * R) * ld * 4;
@@ -190,21 +181,6 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
                         mbar_arrive_expect_tx(&ffull[s], 2 * bytes);
                         bulk_g2s(dst, cost_b + (size_t)c * R * ld * 4, bytes, &ffull[s]);
                         bulk_g2s(dst + tile_bytes, nz_b + (size_t)c * R * ld * 4, bytes, &ffull[s]);
-                        size_t lo = (size_t)c * quota, hi = lo + quota;
-                        if (lo > pbytes) lo = pbytes;
-                        if (hi > pbytes) hi = pbytes;
-                        if (hi > lo) {
-                            for (size_t o = lo; o < hi; o += kFeedZeroBytes)
-                                bulk_s2g(path_b + o, smem + kFeedOffZero, (uint32_t)min((size_t)kFeedZeroBytes, hi - o));
-                            bulk_commit();
-                        }
-                    }
-                    if (path_b) {
-                        // the DP CTA scatters the ones only after the zeros have landed
-                        bulk_wait_all();
-                        fence_proxy_async_all();
-                        __threadfence();
-                        atomicAdd(p.zero_flags + b, (uint32_t)kZeroParts);
                     }
                 }
                 __syncwarp();
@@ -212,6 +188,12 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
                 // ---- appliers: cost + (std * noise) * scale, rounded after every operation (models.py:1242-1247),
                 //      from this CTA's stage straight into the partner's ----
                 const int gl = warp * 32 + lane;
+                long long facc[4] = {0, 0, 0, 0};   // diagnostics: cycles waiting for the loads, reading, waiting for the credit, storing
+                // the first chunks of the draw: into L2 right away (one 128-byte line per thread and chunk)
+                for (int c = 0; c < kFeedAhead && c < n_chunks; ++c) {
+                    const int pbytes = min(R, t_y - c * R) * ld * 4;
+                    if (gl * 128 < pbytes) prefetch_l2(nz_b + (size_t)c * R * ld * 4 + gl * 128);
+                }
                 for (int c = 0; c < n_chunks; ++c) {
                     const uint32_t g = g0 + (uint32_t)c, s = g % kFeedStages, u = g / kFeedStages;
                     const uint32_t st = g % n_stages, ud = g / n_stages;
@@ -223,7 +205,9 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
                         const int pbytes = min(R, t_y - (c + kFeedAhead) * R) * ld * 4;
                         if (gl * 128 < pbytes) prefetch_l2(nz_b + (size_t)(c + kFeedAhead) * R * ld * 4 + gl * 128);
                     }
+                    const long long f0 = MAS_TR(fp.tc) ? clock64() : 0;
                     mbar_wait(&ffull[s], u & 1u);
+                    const long long f1 = MAS_TR(fp.tc) ? clock64() : 0;
                     constexpr int KQ = (R * 64 + HT - 1) / HT;   // items per thread and chunk at the widest plane (256 floats)
                     float4 cv[KQ], nv[KQ];
 #pragma unroll
@@ -231,7 +215,10 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
                         if (gl + k * HT < n4) cv[k] = c4[k * HT], nv[k] = z4[k * HT];
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&fempty[s]);            // this warp has read the stage
-                    mbar_wait_acq_cluster(&credit[st], (ud & 1u) ^ 1u);   // the partner has consumed the stage's previous tile
+                    const long long f2 = MAS_TR(fp.tc) ? clock64() : 0;
+                    if (lane == 0) mbar_wait_acq_cluster(&credit[st], (ud & 1u) ^ 1u);   // the partner has consumed the stage's previous tile
+                    __syncwarp();
+                    const long long f3 = MAS_TR(fp.tc) ? clock64() : 0;
                     const uint32_t dst = r_stage0 + st * p.stage_bytes + (uint32_t)gl * 16u;
 #pragma unroll
                     for (int k = 0; k < KQ; ++k)
@@ -245,7 +232,13 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
                             // release-arrive per warp and tile cost the feeder 1.9 us per chunk)
                             dsm_st_async_v4(dst + (uint32_t)(k * HT) * 16u, cv[k], r_full0 + st * 8u);
                         }
+                    if (MAS_TR(fp.tc)) {
+                        const long long f4 = clock64();
+                        facc[0] += f1 - f0, facc[1] += f2 - f1, facc[2] += f3 - f2, facc[3] += f4 - f3;
+                    }
                 }
+                if (MAS_TR(fp.tc) && gl == 0)
+                    for (int j = 0; j < 4; ++j) fp.tc.trace[40960 + (size_t)b * 16 + 12 + j] = (unsigned long long)facc[j];
             }
             // does the DP want the tiles once more (exact pass after a non-finite cost)?
             mbar_wait_acq_cluster(verdict, n_verdicts & 1u);
@@ -495,8 +488,9 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     fp.dp.trace = fp.tc.trace;
     fp.dp.flag_tiles = m_tiles;
     // the contraction-only CTAs zero-fill the path planes when there are enough of them to do it in time
-    // (with feeders: the feeder CTA of the pair zero-fills its partner's plane)
-    const bool offload = path_out && (feed || (cf.fused_zero_offload && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1));
+    // (with feeders the DP CTA zero-fills its own plane: its bulk-copy engine has nothing else to do, while the
+    // feeder's carries the tile loads -- zero-filling from there cost 13 us at config 2)
+    const bool offload = path_out && !feed && cf.fused_zero_offload && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1;
     fp.dp.zero_flags = offload ? flags + (size_t)B * m_tiles : nullptr;
     fp.dp.zero_queue = flags + (size_t)B * (m_tiles + 1);
     fp.grid_bar = flags + (size_t)B * (m_tiles + 1) + 1;
