@@ -384,11 +384,16 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     MAS_FUSED_CASE(2, 2, true)
     MAS_FUSED_CASE(3, 2, true)
     MAS_FUSED_CASE(4, 2, true)
+#ifdef MAS_TRACE
+    // A/B variants, trace build only (both measured slower): four value warps with two columns
+    // each (MAS_DP_WARPS=4), single-role DP warps (MAS_DP_VK=0).  In the product build those knobs make the call
+    // fall back to separate launches.
     MAS_FUSED_CASE(2, 4, true)
     MAS_FUSED_CASE(1, 2, false)
     MAS_FUSED_CASE(2, 2, false)
     MAS_FUSED_CASE(3, 2, false)
     MAS_FUSED_CASE(4, 2, false)
+#endif
     MAS_NOISE_CASE(1)
     MAS_NOISE_CASE(2)
     MAS_NOISE_CASE(3)
