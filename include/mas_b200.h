@@ -124,10 +124,12 @@ int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p,
  *   - neg_cent_out: optional [B,T,S] float32 copy of the cost actually aligned (with noise: the noised
  *     cost; without this request the noised plane is never written -- the DP adds the noise on the fly).
  *   - path_out may be NULL (compact outputs only), as in mas_maximum_path_f32.
- *   - S <= 256 and no neg_cent_out request: ONE kernel (after the prior preparation) runs contraction and DP --
- *     concurrently without noise; with noise around a grid barrier, B <= 74 (the statistics of models.py:1243
- *     must exist before the first DP row).  Cooperative launch: needs the whole GPU like any persistent kernel;
- *     where the context cannot hold the grid (MPS / MIG limits) the same work runs as separate launches.
+ *   - S <= 256 (any T, no multiple-of-4 requirement) and no neg_cent_out request: ONE kernel (after the prior
+ *     preparation) runs contraction and DP -- concurrently without noise; with noise around a grid barrier (the
+ *     statistics of models.py:1243 must exist before the first DP row), any batch size: B <= 74 with 16-byte rows
+ *     of the draw runs {DP CTA, noise feeder CTA} pairs, larger batches noise-helper warps inside the DP CTAs.
+ *     Cooperative launch: needs the whole GPU like any persistent kernel; where the context cannot hold the grid
+ *     (MPS / MIG limits) the same work runs as separate launches.
  */
 size_t mas_fused_align_workspace_bytes(int B, int D, int T, int S, int with_noise);
 int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,

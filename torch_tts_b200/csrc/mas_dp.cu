@@ -1,6 +1,6 @@
 // mas_dp.cu -- standalone launch of the MAS forward DP + backtrack (role code in mas_dp.cuh),
 // the shared-memory plan, and the small helper kernels (lengths from mask, launch order, expand).
-#include "mas_dp.cuh"
+#include "mas_dp_launch.cuh"
 
 namespace mas {
 
@@ -118,16 +118,6 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int ld, int stages_hint, int 
     return true;
 }
 
-template <int C, int R, int W, bool kVec, bool kNoise, bool kVK>
-__global__ void __launch_bounds__(dp_threads(W, kVK), 1) mas_dp_kernel(const DpParams p)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int b = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
-    uint32_t g_base = 0;
-    dp_role_init(p, smem, threadIdx.x, kDpBar);
-    dp_role<C, R, W, kVec, kNoise, kVK>(p, smem, b, blockIdx.x, g_base, threadIdx.x, kDpBar);
-}
-
 // ---------------------------------------------------------------------------
 // lengths from the dense mask (reference __init__.py:16-17)
 // ---------------------------------------------------------------------------
@@ -210,43 +200,6 @@ size_t dp_workspace_bytes(int B, int T, int S)
         hop = pl.ws_hop_bytes > hop ? pl.ws_hop_bytes : hop;
     }
     return align_up((size_t)B * 4, 256) + align_up(bits, 256) + align_up(hop, 256);
-}
-
-template <int C, int R, int W, bool kVec, bool kNoise, bool kVK = false>
-static int launch_dp_cv(const DpPlan &pl, cudaStream_t stream)
-{
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    MAS_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev != configured_dev) {
-        MAS_CUDA_TRY(cudaFuncSetAttribute(mas_dp_kernel<C, R, W, kVec, kNoise, kVK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kSmemBudget));
-        configured_dev = dev;
-    }
-    mas_dp_kernel<C, R, W, kVec, kNoise, kVK><<<pl.p.B, dp_threads(W, kVK), pl.smem_bytes, stream>>>(pl.p);
-    note_launch();
-    MAS_CUDA_TRY(cudaGetLastError());
-    return MAS_OK;
-}
-
-template <int C, int R, int W>
-static int launch_dp_c(const DpPlan &pl, cudaStream_t stream)
-{
-    // vector cost loads need every tile row 16-byte aligned in shared memory
-    const bool vec = (pl.p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(pl.p.neg_cent) & 15) == 0);
-    if (pl.p.noise) {
-        // noise applied while the cost streams in: vector path only (dp_noise_supported)
-        if (!vec || (reinterpret_cast<uintptr_t>(pl.p.noise) & 15)) return MAS_ERR_UNSUPPORTED_SHAPE;
-        return launch_dp_cv<C, R, W, true, true>(pl, stream);
-    }
-    if (pl.p.vk) {
-        if (!vec) return MAS_ERR_UNSUPPORTED_SHAPE;
-        if constexpr (((W == 2 && C <= 4) || (W == 4 && C == 2)) && R == 32)
-            return launch_dp_cv<C, R, W, true, false, true>(pl, stream);
-        else
-            return MAS_ERR_UNSUPPORTED_SHAPE;
-    }
-    return vec ? launch_dp_cv<C, R, W, true, false>(pl, stream) : launch_dp_cv<C, R, W, false, false>(pl, stream);
 }
 
 // fills pl (shared-memory plan + parameters) without launching; `order_out` receives the workspace slot
@@ -338,16 +291,21 @@ int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, v
         p.order = nullptr;
     }
     // (columns per thread, chunk rows, DP warps): W = 2 covers S <= 512, W = 4 the rest
+    rc = dp_dispatch_narrow(pl, pl.C, stream);
+    if (rc == kDpNoCase) rc = dp_dispatch_wide(pl, pl.C, stream);
+    if (rc == kDpNoCase) rc = dp_dispatch_tall(pl, pl.C, stream);
+    return rc == kDpNoCase ? MAS_ERR_UNSUPPORTED_SHAPE : rc;
+}
+
+int dp_dispatch_narrow(const DpPlan &pl, int C, cudaStream_t stream)
+{
+    const DpParams &p = pl.p;
 #define MAS_DP_CASE(CC, RR, WW) \
-    if (pl.C == CC && p.R == RR && p.W == WW) return launch_dp_c<CC, RR, WW>(pl, stream);
+    if (C == CC && p.R == RR && p.W == WW) return launch_dp_c<CC, RR, WW>(pl, stream);
     MAS_DP_CASE(1, 32, 2) MAS_DP_CASE(2, 32, 2) MAS_DP_CASE(3, 32, 2) MAS_DP_CASE(4, 32, 2)
     MAS_DP_CASE(5, 16, 2) MAS_DP_CASE(6, 16, 2) MAS_DP_CASE(7, 16, 2) MAS_DP_CASE(8, 16, 2)
-    MAS_DP_CASE(2, 32, 4)   // MAS_DP_WARPS=4 at S <= 256: the A/B partner of the default
-    MAS_DP_CASE(5, 8, 4) MAS_DP_CASE(6, 8, 4) MAS_DP_CASE(7, 8, 4) MAS_DP_CASE(8, 8, 4)
-    MAS_DP_CASE(5, 16, 4) MAS_DP_CASE(6, 16, 4) MAS_DP_CASE(7, 16, 4) MAS_DP_CASE(8, 16, 4)   // bits / hops spilled
-    MAS_DP_CASE(5, 32, 2) MAS_DP_CASE(6, 32, 2) MAS_DP_CASE(7, 32, 2) MAS_DP_CASE(8, 32, 2)
 #undef MAS_DP_CASE
-    return MAS_ERR_UNSUPPORTED_SHAPE;
+    return kDpNoCase;
 }
 
 int lengths_launch(const float *mask, int32_t *t_ys, int32_t *t_xs, int B, int T, int S, cudaStream_t stream)
