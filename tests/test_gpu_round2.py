@@ -238,3 +238,45 @@ def test_generate_path_fractional_durations(cuda_device):
     dur[1, 0, 1] = 3.0e38
     got = tts.generate_path(dur.to(cuda_device), mask.to(cuda_device))
     assert torch.isfinite(got).all() and float(got.sum(-1).max()) <= 1.0
+
+
+# --------------------------------------------------------------------------
+# protocol edges of the single-launch noise kernel (feeder pairs for B <= 74, helper warps above)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [6, 80])
+def test_noise_kernel_with_an_invalid_utterance(cuda_device, mas_env, B):
+    """An utterance the reference leaves undefined (t_x > t_y) is skipped by the DP CTA and by its feeder alike: zero
+    path, zero durations, idx -1, status 1 -- and the others are aligned exactly as by the separate launches."""
+    S, T = 64, 256
+    t_x, t_y, host, dev = _inputs(B, S, T, seed=17, dev=cuda_device)
+    bad = 2
+    x_mask, y_mask = host[3].clone(), host[4].clone()
+    y_mask[bad, 0, 5:] = 0.0          # 5 mel frames, far fewer than the text tokens
+    x_mask[bad, 0, :40] = 1.0
+    dev = dev[:3] + (x_mask.to(cuda_device), y_mask.to(cuda_device))
+    noise = torch.randn((B, T, S), generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    (a, w, (idx, dur, status)), n = _launches(lambda: tts.align(*dev, 0.01, noise, return_compact=True))
+    assert n == 2
+    assert int(status[bad]) == 1 and int(status.sum()) == 1
+    assert not a[bad].any() and not dur[bad].any() and bool((idx[bad] == -1).all())
+    mas_env(MAS_NOISE_FUSED=0)
+    a3, w3, (idx3, dur3, status3) = tts.align(*dev, 0.01, noise, return_compact=True)
+    assert torch.equal(idx, idx3) and torch.equal(dur, dur3) and torch.equal(a, a3) and torch.equal(status, status3)
+
+
+@pytest.mark.parametrize("B", [5, 80])
+def test_noise_kernel_with_a_non_finite_input(cuda_device, mas_env, B):
+    """A NaN in z_p makes the std -- and with it every cost of the batch -- NaN (models.py:1243): every utterance takes
+    the exact second pass, i.e. the DP asks its feeder (or its helper warps) for all the tiles once more.  Same paths
+    as the separate launches, which implement the reference's compare-select on NaN the same way."""
+    S, T = 96, 320
+    t_x, t_y, host, dev = _inputs(B, S, T, seed=19, dev=cuda_device)
+    z = dev[0].clone()
+    z[1, 3, 7] = float("nan")
+    dev = (z,) + dev[1:]
+    noise = torch.randn((B, T, S), generator=torch.Generator().manual_seed(6)).to(cuda_device)
+    (a, w, (idx, dur, status)), n = _launches(lambda: tts.align(*dev, 0.01, noise, return_compact=True))
+    assert n == 2 and (status == 0).all() and torch.equal(dur.sum(1).cpu(), t_y)
+    mas_env(MAS_NOISE_FUSED=0)
+    a3, w3, (idx3, dur3, status3) = tts.align(*dev, 0.01, noise, return_compact=True)
+    assert torch.equal(idx, idx3) and torch.equal(dur, dur3) and torch.equal(a, a3)
