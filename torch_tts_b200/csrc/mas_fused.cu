@@ -495,7 +495,9 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     // the contraction-only CTAs zero-fill the path planes when there are enough of them to do it in time
     // (with feeders the DP CTA zero-fills its own plane: its bulk-copy engine has nothing else to do.  Zero-filling
     // from the feeder cost 13 us at config 2 through its bulk-copy engine, which carries the tile loads, and 9 us
-    // with plain stores from its applier warps.)
+    // with plain stores from its applier warps; sharing zero_fill_role's work queue between the 20 CTAs that are in
+    // no pair at config 2 and the DP CTAs' producer lanes 9 us -- and 4 us even with the queue unused, from what the
+    // extra code did to the DP role's register allocation.)
     const bool offload = path_out && !feed && cf.fused_zero_offload && (grid - n_dp) * 2 >= n_dp && utts_per_cta == 1;
     fp.dp.zero_flags = offload ? flags + (size_t)B * m_tiles : nullptr;
     fp.dp.zero_queue = flags + (size_t)B * (m_tiles + 1);
