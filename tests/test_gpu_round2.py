@@ -112,6 +112,57 @@ def test_arbitrary_shapes_take_the_one_kernel_path(cuda_device, B, S, T, scale):
     assert torch.equal(w.sum((1, 2)).cpu(), w_ref.sum((1, 2)))
 
 
+@pytest.mark.parametrize("B,S,T", [(4, 600, 4000), (3, 300, 1000), (2, 513, 701), (2, 1000, 1100), (5, 431, 1500), (80, 257, 300)])
+def test_wide_text_takes_the_one_kernel_path(cuda_device, B, S, T):
+    """256 < S <= 1024 (several column blocks per mel tile, single-role DP teams of two or four warps, spilled decision
+    words for long utterances -- BASELINE config 4 is (32, 600, 4000)): prior preparation + ONE fused kernel, same
+    alignment as with the explicit cost plane, exact MAS optimum of that cost, parity with the reference expression."""
+    t_x, t_y, host, dev = _inputs(B, S, T, seed=S + T, dev=cuda_device)
+    (attn, w, (idx, dur, status)), n = _launches(lambda: tts.align(*dev, return_compact=True))
+    assert n == 2, n
+    attn2, w2, (idx2, dur2, status2), nc = tts.align(*dev, return_compact=True, return_neg_cent=True)
+    assert (status == 0).all() and torch.equal(dur.sum(1).cpu(), t_y)
+    assert torch.equal(idx, idx2) and torch.equal(dur, dur2) and torch.equal(attn, attn2)
+    assert torch.equal(tts.expand_path(idx, S), attn.squeeze(1))
+    sel = list(range(min(B, 4)))
+    want = mas_oracle.maximum_path_c(nc[sel].cpu().numpy(), t_y[sel].numpy(), t_x[sel].numpy())
+    assert np.array_equal(attn[sel].squeeze(1).cpu().numpy().astype(np.int32), want)
+    z_p, m_p, logs_p, x_mask, y_mask = (t[sel] for t in host)
+    attn_ref, w_ref, nc_ref = mas_oracle.align_torch(z_p, m_p, logs_p, x_mask, y_mask, None, None)
+    assert ((nc[sel].cpu() - nc_ref).abs() / nc_ref.abs().clamp_min(1.0)).max().item() < 1e-4
+    assert (attn[sel].cpu() == attn_ref).float().mean().item() >= MIN_AGREE
+
+
+@pytest.mark.parametrize("B,S,T", [(80, 257, 300), (160, 131, 300), (100, 33, 700), (3, 1001, 1515)])
+@pytest.mark.parametrize("with_noise", [False, True])
+def test_explicit_cost_plane_with_unaligned_rows(cuda_device, B, S, T, with_noise):
+    """S % 4 != 0 and enough units that every contraction CTA takes several rounds: tts.neg_cent and
+    align(return_neg_cent=True) store 16-byte rows into the padded workspace plane and pack them afterwards.  The
+    plane is the same run after run, matches the reference expression, and the path is its exact MAS optimum."""
+    t_x, t_y, host, dev = _inputs(B, S, T, seed=S * T, dev=cuda_device)
+    z_p, m_p, logs_p, x_mask, y_mask = dev
+    nc0 = tts.neg_cent(z_p, m_p, logs_p)
+    for _ in range(3):
+        assert torch.equal(tts.neg_cent(z_p, m_p, logs_p), nc0)
+    want = mas_oracle.neg_cent_torch(*(t[:6] for t in host[:3]))
+    assert ((nc0[:6].cpu() - want).abs() / want.abs().clamp_min(1.0)).max().item() < 1e-4
+    noise = torch.randn((B, T, S), generator=torch.Generator().manual_seed(5)).to(cuda_device) if with_noise else None
+    scale = 0.01 if with_noise else None
+    attn, w, (idx, dur, status), nc = tts.align(*dev, scale, noise, return_compact=True, return_neg_cent=True)
+    if with_noise:
+        std = nc0.double().std().float()
+        assert ((nc - (nc0 + std * noise * 0.01)).abs() / nc0.abs().clamp_min(1.0)).max().item() < 1e-5
+    else:
+        assert torch.equal(nc, nc0)
+    assert (status == 0).all() and torch.equal(dur.sum(1).cpu(), t_y)
+    sel = list(range(0, B, max(1, B // 5)))
+    want_path = mas_oracle.maximum_path_c(nc[sel].cpu().numpy(), t_y[sel].numpy(), t_x[sel].numpy())
+    assert np.array_equal(attn[sel].squeeze(1).cpu().numpy().astype(np.int32), want_path)
+    # and the private-plane route (one kernel, or contraction + pass + DP when the noise kernel does not cover S)
+    attn2, w2, (idx2, dur2, status2) = tts.align(*dev, scale, noise, return_compact=True)
+    assert torch.equal(idx, idx2) and torch.equal(dur, dur2)
+
+
 # --------------------------------------------------------------------------
 # noise-scaled alignment in one launch
 # --------------------------------------------------------------------------

@@ -86,7 +86,7 @@ size_t dp_workspace_bytes(int B, int T, int S);
 int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
               int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace, size_t workspace_bytes, int B,
               int T, int S, cudaStream_t stream, const float *noise = nullptr, const double *stats = nullptr,
-              float noise_scale = 0.f);
+              float noise_scale = 0.f, int ld = 0);
 bool dp_noise_supported(const float *neg_cent, const float *noise, int S);
 int lengths_launch(const float *mask, int32_t *t_ys, int32_t *t_xs, int B, int T, int S, cudaStream_t stream);
 int expand_launch(const int32_t *idx, void *path_out, int path_dtype, int B, int T, int S, cudaStream_t stream);
@@ -102,7 +102,9 @@ int idx_from_durations_launch(const float *dur_f, const int32_t *t_xs, const int
 size_t cost_workspace_bytes(int B, int D, int T, int S);
 int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
                 const int32_t *t_ys, void *workspace, size_t workspace_bytes, int B, int D, int T, int S,
-                cudaStream_t stream);
+                cudaStream_t stream, int ld = 0);
+int rows_launch(const float *src, int ld_src, const float *noise, const double *stats, float scale, float *dst,
+                int ld_dst, size_t rows, int S, cudaStream_t stream);
 int add_noise_launch(const float *nc, const float *noise, const double *stats, float scale, float *out, size_t n,
                      cudaStream_t stream);
 
@@ -189,7 +191,8 @@ int mas_maximum_path_f32(const float *neg_cent, const int32_t *t_ys, const int32
 size_t mas_neg_cent_workspace_bytes(int B, int D, int T, int S)
 {
     if (check_shape(B, T, S) != MAS_OK || D < 1) return 0;
-    return cost_workspace_bytes(B, D, T, S);
+    // S % 4 != 0: the contraction stores 16-byte rows into a padded plane in the workspace, a second kernel packs them
+    return align_up(cost_workspace_bytes(B, D, T, S), 256) + (S % 4 ? fused_plane_bytes(B, T, S) : 0);
 }
 
 int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
@@ -201,8 +204,16 @@ int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p, fl
     if (D < 1) return MAS_ERR_BAD_SHAPE;
     if (!aligned16(z_p) || !aligned16(m_p) || !aligned16(logs_p) || !aligned16(neg_cent_out) || !aligned16(workspace))
         return MAS_ERR_ALIGNMENT;
-    return cost_launch(z_p, m_p, logs_p, neg_cent_out, stats_out, nullptr, workspace, workspace_bytes, B, D, T, S,
-                       static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (S % 4 == 0)
+        return cost_launch(z_p, m_p, logs_p, neg_cent_out, stats_out, nullptr, workspace, workspace_bytes, B, D, T, S, st);
+    if (!workspace || workspace_bytes < mas_neg_cent_workspace_bytes(B, D, T, S)) return MAS_ERR_WORKSPACE;
+    const size_t cost_ws = align_up(cost_workspace_bytes(B, D, T, S), 256);
+    float *plane = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + cost_ws);
+    const int ld = (S + 3) & ~3;
+    rc = cost_launch(z_p, m_p, logs_p, plane, stats_out, nullptr, workspace, cost_ws, B, D, T, S, st, ld);
+    if (rc) return rc;
+    return rows_launch(plane, ld, nullptr, nullptr, 0.f, neg_cent_out, S, (size_t)B * T, S, st);
 }
 
 // fused workspace layout: [cost ws][stats 256 B][private cost plane, rows padded to 16 bytes][dp ws][flags]
@@ -248,14 +259,28 @@ int mas_fused_align_f32(const float *z_p, const float *m_p, const float *logs_p,
         // the cooperative grid does not fit this context: the same work as separate launches below
     }
     // mel tiles wholly past t_y are skipped only when the plane is private scratch: a caller who asked for
-    // neg_cent_out gets every cell the reference would compute
-    float *nc = neg_cent_out ? neg_cent_out : plane;
+    // neg_cent_out gets every cell the reference would compute.  The contraction stores rows of 16-byte multiples:
+    // S % 4 != 0 goes through the padded plane of the workspace.
+    const int ld = (S + 3) & ~3;
+    const bool packed = (ld == S);
+    float *nc = (neg_cent_out && packed) ? neg_cent_out : plane;
     rc = cost_launch(z_p, m_p, logs_p, nc, noise ? stats : nullptr, neg_cent_out ? nullptr : t_ys, ws, cost_ws, B, D,
-                     T, S, st);
+                     T, S, st, ld);
     if (rc) return rc;
     if (config().stage == 1) return MAS_OK;
+    if (!packed) {
+        // pack the rows into the caller's tensor, or (private plane) add the noise in place; the DP reads either pitch
+        if (neg_cent_out || noise) {
+            float *dst = neg_cent_out ? neg_cent_out : plane;
+            rc = rows_launch(plane, ld, noise, stats, noise_scale, dst, neg_cent_out ? S : ld, (size_t)B * T, S, st);
+            if (rc) return rc;
+            noise = nullptr;
+        }
+        return dp_launch(neg_cent_out ? neg_cent_out : plane, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out,
+                         status_out, dp_ws, dp_ws_bytes, B, T, S, st, nullptr, nullptr, 0.f, neg_cent_out ? S : ld);
+    }
     if (noise && (neg_cent_out || !dp_noise_supported(nc, noise, S))) {
-        // the caller wants the noised cost plane itself (or the rows are not 16-byte): one more pass
+        // the caller wants the noised cost plane itself (or the noise rows are not 16-byte aligned): one more pass
         rc = add_noise_launch(nc, noise, stats, noise_scale, nc, (size_t)B * T * S, st);
         if (rc) return rc;
         noise = nullptr;

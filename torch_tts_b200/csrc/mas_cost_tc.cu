@@ -169,12 +169,17 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
 
 int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, float *neg_cent_out, double *stats_out,
                    const int32_t *t_ys, void *workspace, size_t workspace_bytes, int B, int D, int T, int S,
-                   cudaStream_t stream)
+                   cudaStream_t stream, int ld)
 {
     TcPlan plan;
     int rc = cost_tc_prepare(plan, z_p, m_p, logs_p, neg_cent_out, stats_out, t_ys, workspace, workspace_bytes, B, D, T,
-                             S, nullptr, 0, stream);
+                             S, nullptr, 0, stream, ld);
     if (rc) return rc;
+    // The plain-store epilogue (no tensor map for the output) is an experiment of the trace build: with several
+    // rounds of units per CTA it returned whole 32-row groups with a K block's worth of error (run-dependent,
+    // tools/debug_nc*.py in round 2), so product launches always store through the tensor map.
+    if (!kTrace && !plan.p.out_tma)
+        return MAS_ERR_UNSUPPORTED_SHAPE;
     static thread_local int configured_dev = -1;
     int dev = 0, sms = 148;
     MAS_CUDA_TRY(cudaGetDevice(&dev));

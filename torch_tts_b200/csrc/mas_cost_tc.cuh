@@ -310,7 +310,11 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
     uint64_t *bias_full = bars + 32;       // [2] bias buffer written by warp 2
     uint64_t *bias_empty = bars + 34;      // [2] bias buffer released by the 4 epilogue warps
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 36);
-    uint32_t *pub_cnt = tmem_slot + 1;     // [2] epilogue warps whose stores of a unit have completed
+    uint32_t *pub_cnt = tmem_slot + 1;     // [4] epilogue warps whose stores of a unit have completed, slot = unit number % 4:
+                                           // a fast epilogue warp can be publishing unit k + 2 while a slow one has not yet
+                                           // published unit k (they release the accumulator before they publish), so two
+                                           // slots alias -- seen with the 16-column units of S = 257, whose tiles went out
+                                           // with a quarter of their rows still in flight
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -335,6 +339,7 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             mbar_init(&bias_full[i], 1);
             mbar_init(&bias_empty[i], 4);
             pub_cnt[i] = 0u;
+            pub_cnt[i + 2] = 0u;
         }
         fence_mbar_init();
         if (p.z_tma) tma_prefetch_desc(tm_z);
@@ -562,7 +567,10 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             if (atomicAdd(&pub_cnt[par], 1u) == 3u) {
                 pub_cnt[par] = 0u;
                 __threadfence();
-                st_release_gpu(flag, 1u);
+                if (p.n_blocks > 1)
+                    atomicAdd(flag, 1u);          // one publication per column block of the tile
+                else
+                    st_release_gpu(flag, 1u);
                 if (MAS_TR(p)) {
                     unsigned long long *tr = p.trace + (size_t)blockIdx.x * 64;
                     const unsigned long long n = tr[0] + 1;   // word 0: count, then one time per published tile
@@ -588,6 +596,9 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
             uint64_t us0 = 0ull, us1 = 0ull, uq0 = 0ull, uq1 = 0ull;   // packed fp32 {sum, sum} / {sum sq, sum sq} of the unit
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t r[32];
+                // tcgen05.ld is .sync.aligned: every lane of the warp arrives here together (the plain-store path
+                // below predicates its stores on the lane's row)
+                __syncwarp();
                 tmem_ld32(taddr + c0, r);
                 tmem_ld_wait();
                 float v[32];
@@ -677,16 +688,16 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     if (p.out_tma && !MAS_DBG(p, 2)) {
                         if MAS_DBG(p, 64) {
                             pend_flag = flag;  // experiment: publish after the first store of the next unit
-                            pend_par = a;
+                            pend_par = nt & 3u;
                         } else {
                             // nothing else to do until the next accumulator fills: wait for the stores to land
                             // and hand the tile to the DP now rather than one unit later
                             bulk_wait_all();
-                            publish(flag, a);
+                            publish(flag, nt & 3u);
                         }
                     } else {
                         __threadfence();
-                        publish(flag, a);
+                        publish(flag, nt & 3u);
                     }
                 }
             }

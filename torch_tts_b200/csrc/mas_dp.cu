@@ -238,6 +238,7 @@ int dp_prepare(DpPlan &pl, const float *neg_cent, const int32_t *t_ys, const int
     p.status = status_out;
     p.flags = nullptr;
     p.flag_tiles = 0;
+    p.flag_need = 1;
     p.zero_flags = nullptr;
     p.zero_queue = nullptr;
     p.trace = trace_buffer();
@@ -266,12 +267,13 @@ bool dp_noise_supported(const float *neg_cent, const float *noise, int S)
 // squares} of all cost cells on the device (the contraction's epilogue wrote them)
 int dp_launch(const float *neg_cent, const int32_t *t_ys, const int32_t *t_xs, void *path_out, int path_dtype,
               int32_t *dur_out, int32_t *idx_out, int32_t *status_out, void *workspace, size_t workspace_bytes, int B,
-              int T, int S, cudaStream_t stream, const float *noise, const double *stats, float noise_scale)
+              int T, int S, cudaStream_t stream, const float *noise, const double *stats, float noise_scale, int ld)
 {
     DpPlan pl;
     int32_t *order = nullptr;
+    if (noise && ld > 0 && ld != S) return MAS_ERR_UNSUPPORTED_SHAPE;   // the noise rows are packed
     int rc = dp_prepare(pl, neg_cent, t_ys, t_xs, path_out, path_dtype, dur_out, idx_out, status_out, workspace,
-                        workspace_bytes, B, T, S, &order, 0, 0, noise != nullptr);
+                        workspace_bytes, B, T, S, &order, 0, 0, noise != nullptr, ld, 0);
     if (rc) return rc;
     DpParams &p = pl.p;
     p.noise = noise;

@@ -65,6 +65,7 @@ struct DpParams {
     int32_t *status;
     uint32_t *flags;        // nullable: [B][flag_tiles] cost-tile-ready flags of the fused kernel (consumed and reset here)
     int flag_tiles;         // mel tiles of 128 rows per utterance
+    int flag_need;          // publications that complete a tile (column blocks of the contraction: 1 for S <= 256)
     uint32_t *zero_queue;   // fused kernel: work counter of the zero-fill role (cleared with the flags)
     uint32_t *zero_flags;   // nullable: [B] set by whoever zero-fills the path plane of an utterance (fused kernel: the
                             // contraction CTAs, once they run out of tiles); consumed and reset here
@@ -687,7 +688,7 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
                 if (p.flags && pass == 0 && (row0 & 127) == 0) {
                     // fused kernel: the cost tile holding these rows must have been published; consume the flag
                     uint32_t *f = p.flags + (size_t)b * p.flag_tiles + (row0 >> 7);
-                    while (ld_acquire_gpu(f) == 0u) __nanosleep(64);
+                    while (ld_acquire_gpu(f) < (uint32_t)p.flag_need) __nanosleep(64);
                     *f = 0u;
                     if (MAS_TR(p)) p.trace[12288 + (size_t)b * 32 + 2 + (row0 >> 7)] = globaltimer_ns();
                     fence_proxy_async_all();  // order the bulk (async-proxy) reads below after the acquire

@@ -22,67 +22,10 @@
 // The private cost plane has its own row stride (S rounded up to 4 floats), so S and T are arbitrary.
 #include <atomic>
 
-#include "mas_cost_tc.cuh"
-#include "mas_dp.cuh"
+#include "mas_fused_body.cuh"
 #include "mas_fused.cuh"
 
 namespace mas {
-
-struct FusedParams {
-    TcParams tc;
-    DpParams dp;
-    int n_dp;              // the first n_dp CTAs turn into DP CTAs after their share of the contraction
-    uint32_t *grid_bar;    // noise kernel: grid barrier counter (cleared with the flags)
-    int feed_pairs;        // noise kernel: > 0 = that many CTA pairs run {DP CTA, noise feeder CTA} after the barrier
-    const float *noise;    // noise kernel with feeders: the draw [B][T][S] (16-byte rows), its scale, the statistics
-    float noise_scale;
-    const double *stats;
-};
-
-constexpr int kNoiseHelpWarps = 8;   // helper warps of a DP CTA in the noise kernel (dp_role, kHelp)
-
-template <int C, int R, int W, bool kVK, int kHelp = 0>
-__device__ __forceinline__ void fused_dp_ctas(const FusedParams &fp, unsigned char *smem)
-{
-    // DP CTA j aligns utterances j, j + n_dp, ... on its first dp_threads(W) (+ helper) threads
-    if ((int)threadIdx.x >= dp_threads(W, kVK) + 32 * kHelp) return;
-    const int j = (int)blockIdx.x;
-    uint32_t g_base = 0;
-    dp_role_init(fp.dp, smem, threadIdx.x, kDpBar);
-    for (int b = j; b < fp.dp.B; b += fp.n_dp)
-        dp_role<C, R, W, true, false, kVK, kHelp>(fp.dp, smem, b, j, g_base, threadIdx.x, kDpBar);
-}
-
-template <int C, int R, int W, bool kPair, bool kVK>
-__device__ __forceinline__ void fused_body(const FusedParams &fp, const CUtensorMap *tm_z, const CUtensorMap *tm_out,
-                                           unsigned char *smem)
-{
-    // every CTA starts in the contraction role; the first n_dp CTAs ("hybrid") leave it after seq_k rounds of
-    // units and become the DP CTAs, the others finish the remaining units (unit_index() in cost_tc_role)
-    if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + blockIdx.x] = globaltimer_ns();  // CTA entry
-    if (kPair)
-        cost_tc_role<false, true>(fp.tc, tm_z, tm_out, smem, blockIdx.x >> 1, gridDim.x >> 1);
-    else
-        cost_tc_role<false, false>(fp.tc, tm_z, tm_out, smem, blockIdx.x, gridDim.x);
-    if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 256 + blockIdx.x] = globaltimer_ns();  // contraction role left
-    if ((int)blockIdx.x >= fp.n_dp) {
-        // out of tiles: zero-fill the dense path planes while the DP CTAs are still busy
-        if (fp.dp.zero_flags) zero_fill_role(fp.dp, smem);
-        if (MAS_TR(fp.tc) && threadIdx.x == 0) fp.tc.trace[49152 + 512 + blockIdx.x] = globaltimer_ns();  // zero-fill done
-        return;
-    }
-    fused_dp_ctas<C, R, W, kVK>(fp, smem);
-}
-
-// contraction CTAs in pairs (clusters of 2, n_gemm even); the DP CTAs ignore their cluster
-template <int C, int R, int W, bool kVK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-    mas_fused_pair_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CUtensorMap tm_z,
-                          const __grid_constant__ CUtensorMap tm_out)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    fused_body<C, R, W, true, kVK>(fp, &tm_z, &tm_out, smem);
-}
 
 #ifdef MAS_TRACE
 // single-CTA contraction (cta_group::1), kept for A/B runs in the trace build (MAS_TC_PAIR=0)
@@ -313,14 +256,15 @@ static int padded_ld(int S) { return (S + 3) & ~3; }
 bool fused_supported(int B, int D, int T, int S)
 {
     if (config().no_fused) return false;
-    // the contraction role of the fused kernel takes one column block (S <= 256)
-    return cost_tc_supported(B, D, T, S) && S <= kNMax;
+    // up to four column blocks of 256 text columns (a mel tile is complete when all its blocks have been published)
+    return cost_tc_supported(B, D, T, S);
 }
 
 // noise-scaled alignment in one kernel (any batch size: the DP CTAs apply the noise themselves)
 bool fused_noise_supported(int B, int D, int T, int S)
 {
-    return config().noise_fused && fused_supported(B, D, T, S) && config().dp_vk;
+    // (one column block: the noise kernel's DP roles are the warp-split ones)
+    return config().noise_fused && fused_supported(B, D, T, S) && S <= kNMax && config().dp_vk;
 }
 
 // tile flags [B][m_tiles], the zero-fill flags [B], the zero-fill queue counter, the grid barrier counter
@@ -401,6 +345,8 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
 #undef MAS_FUSED_CASE
 #undef MAS_NOISE_CASE
 #undef MAS_FUSED_PLAIN
+    if (!noise && S > kNMax && pair && !dp.p.vk && dp.p.W == 2) kernel = fused_pair_kernel_wide2(dp.C, dp.p.R);
+    if (!noise && S > kNMax && pair && !dp.p.vk && dp.p.W == 4) kernel = fused_pair_kernel_wide4(dp.C, dp.p.R);
     if (!kernel) return kFusedFallback;
 
     size_t smem = dp.smem_bytes;
@@ -417,14 +363,14 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
         return kFusedFallback;
     }
     const int grid = pair ? (sms & ~1) : sms;
-    const int units = B * (pair ? (m_tiles + 1) / 2 : m_tiles);
+    const int units = B * (pair ? (m_tiles + 1) / 2 : m_tiles) * tc.p.n_blocks;
 
     // Unit schedule: all CTAs take seq_k rounds of units, then the DP CTAs leave.  A small cost model picks
     // seq_k and, for batches larger than 64, between 64 DP CTAs and nearly all of them: the contraction must
     // not end long after the DP could, and the DP must not start long before its tiles exist.
     //   unit: the bytes one SM moves per unit through its TMA path (~60 GB/s) or the MMA time, whichever is longer
     //   DP:   ~ (16 + 10 C) cycles per mel row with the value / origin split, + 8 us per utterance (backtrack, outputs)
-    const int n_kb = tc.p.n_kb, n_cols = (S + 15) & ~15;
+    const int n_kb = tc.p.n_kb, n_cols = S > kNMax ? kNMax : ((S + 15) & ~15);   // (columns of one unit = one column block)
     const double unit_bytes = (double)kBM * D * 4 + (double)n_kb * 2 * (n_cols / per) * kRowBytes + (double)kBM * n_cols * 4;
     const double t_mma = 4.7 * (n_cols / 256.0) * (D / 192.0);
     const double t_u = unit_bytes / 60e3 > t_mma ? unit_bytes / 60e3 : t_mma;
@@ -492,6 +438,7 @@ int fused_launch(const float *z_p, const float *m_p, const float *logs_p, const 
     fp.tc.trace = trace_buffer();
     fp.dp.trace = fp.tc.trace;
     fp.dp.flag_tiles = m_tiles;
+    fp.dp.flag_need = tc.p.n_blocks;          // every column block of a mel tile publishes it once
     // the contraction-only CTAs zero-fill the path planes when there are enough of them to do it in time
     // (with feeders the DP CTA zero-fills its own plane: its bulk-copy engine has nothing else to do.  Zero-filling
     // from the feeder cost 13 us at config 2 through its bulk-copy engine, which carries the tile loads, and 9 us
