@@ -55,6 +55,66 @@ def test_expand_prior_backward_matches_autograd_of_the_matmuls(cuda_device, B, S
         assert float(m_dev.grad[b, :, int(t_x[b]):].abs().sum()) == 0.0
 
 
+def _segsum_reference(g, dur):
+    """fp64 segmented sum on the host: g [B,D,T], dur [B,S] -> [B,D,S]"""
+    B, D, T = g.shape
+    S = dur.shape[1]
+    out = torch.zeros((B, D, S), dtype=torch.float64)
+    g64 = g.double()
+    for b in range(B):
+        start = 0
+        for s in range(S):
+            n = max(int(dur[b, s]), 0)
+            lo, hi = min(start, T), min(start + n, T)
+            if hi > lo:
+                out[b, :, s] = g64[b, :, lo:hi].sum(1)
+            start += n
+    return out
+
+
+@pytest.mark.parametrize("B,D,S,T", [(3, 192, 256, 1024), (2, 80, 97, 332), (2, 33, 600, 2000), (1, 192, 1000, 1100),
+                                     (4, 130, 50, 64), (2, 192, 31, 1000), (2, 64, 77, 301)])
+@pytest.mark.parametrize("two", [True, False])
+def test_prior_backward_kernels_agree(cuda_device, mas_env, B, D, S, T, two):
+    """The channels-on-lanes kernel (tensor-map tiles, T % 4 == 0) and the column-per-thread kernel (any T) add the
+    same frames in the same ascending order: bit-identical to each other, and equal to the fp64 sum within fp32
+    rounding.  Durations include empty columns, one very long segment, and (last utterance) columns past t_y."""
+    g = torch.Generator().manual_seed(B * D + S)
+    dur = torch.zeros((B, S), dtype=torch.int32)
+    for b in range(B):
+        t_y = T if b == 0 else int(torch.randint(S // 2 + 1, T + 1, (1,), generator=g))
+        cuts = torch.sort(torch.randint(0, t_y + 1, (S - 1,), generator=g)).values
+        edges = torch.cat([torch.zeros(1, dtype=torch.long), cuts, torch.tensor([t_y])])
+        dur[b] = (edges[1:] - edges[:-1]).int()
+    if B > 1:   # one column owns nearly everything
+        dur[1] = 0
+        dur[1, S // 3] = T - 3
+        dur[1, S // 3 + 1] = 2
+    gm, gl = torch.randn((B, D, T), generator=g), torch.randn((B, D, T), generator=g)
+    L, p = tts._lib.lib(), tts._lib.ptr
+    gm_d, gl_d, dur_d = gm.to(cuda_device), (gl.to(cuda_device) if two else None), dur.to(cuda_device)
+
+    def run():
+        out_m = torch.full((B, D, S), float("nan"), device=cuda_device)
+        out_l = torch.full((B, D, S), float("nan"), device=cuda_device) if two else None
+        rc = L.mas_expand_prior_backward_f32(p(gm_d), p(gl_d), p(dur_d), p(out_m), p(out_l), B, D, T, S,
+                                             torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        return out_m, out_l
+
+    new_m, new_l = run()
+    mas_env(MAS_SEGSUM=0)
+    old_m, old_l = run()
+    assert torch.equal(new_m, old_m)
+    want_m = _segsum_reference(gm, dur)
+    assert (new_m.cpu().double() - want_m).abs().max().item() <= 1e-5 * max(1.0, want_m.abs().max().item())
+    if two:
+        assert torch.equal(new_l, old_l)
+        want_l = _segsum_reference(gl, dur)
+        assert (new_l.cpu().double() - want_l).abs().max().item() <= 1e-5 * max(1.0, want_l.abs().max().item())
+
+
 @pytest.mark.parametrize("B,S,T,ragged", [(5, 80, 320, True), (2, 256, 1024, False)])
 def test_logw(cuda_device, B, S, T, ragged):
     t_x, t_y, m_p, logs_p, x_mask, attn, idx, dur = _aligned(B, S, T, ragged, cuda_device, seed=9, D=8)

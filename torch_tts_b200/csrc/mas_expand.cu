@@ -273,9 +273,15 @@ int expand_prior_launch(const float *m_p, const float *logs_p, const int32_t *id
     return MAS_OK;
 }
 
+// mas_segsum.cu: channels on the lanes, tiles through the tensor-map engine (T % 4 == 0, 16-byte aligned gradients)
+bool segsum_try_launch(const float *g_m, const float *g_logs, const int32_t *dur, float *g_m_p, float *g_logs_p, int B,
+                       int D, int T, int S, cudaStream_t stream, int *rc);
+
 int expand_prior_backward_launch(const float *g_m, const float *g_logs, const int32_t *dur, float *g_m_p, float *g_logs_p,
                                  int B, int D, int T, int S, cudaStream_t stream)
 {
+    int rc = MAS_OK;
+    if (config().segsum && segsum_try_launch(g_m, g_logs, dur, g_m_p, g_logs_p, B, D, T, S, stream, &rc)) return rc;
     const dim3 grid((unsigned)((D + kScatterD - 1) / kScatterD), (unsigned)B);
 #define MAS_SCATTER(TWO, COLS) \
     mas_scatter_prior_kernel<TWO, COLS><<<grid, kScatterThreads, 0, stream>>>(g_m, g_logs, dur, g_m_p, g_logs_p, D, T, S)
