@@ -40,6 +40,7 @@ static void read_config()
     c.noise_fused = env_int("MAS_NOISE_FUSED", 1);
     c.noise_feed = env_int("MAS_NOISE_FEED", 1);
     c.segsum = env_int("MAS_SEGSUM", 1);
+    c.seg_stages = env_int("MAS_SEG_STAGES", 0);
     c.stage = env_int("MAS_STAGE", 0);
     c.tc_pair = 1;
     if (kTrace) {

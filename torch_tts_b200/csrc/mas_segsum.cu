@@ -21,14 +21,14 @@ bool make_tmap_f32_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t 
                       uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool swizzle128);
 
 constexpr int kSegFrames = 32;     // frames per tile row: 128 bytes, one swizzle atom
-constexpr int kSegStages = 3;
+constexpr int kSegStages = 8;     // most tiles in the ring (the launch picks how many are used)
 constexpr int kSegRing = 64;      // parked column sums per warp (at most 4 close per step of 4 frames, 32 leave at a time)
 constexpr int kSegMaxWarps = 4;    // consumer warps per CTA (32 channels each); one more warp issues the loads
 
 struct SegParams {
     const int32_t *dur;
     float *g_m_p, *g_logs_p;
-    int D, T, S, nw;
+    int D, T, S, nw, stages;
 };
 
 // 32 parked sums x up to 32 channels of one warp -> g_in (lane = one non-empty column, neighbouring lanes are
@@ -49,17 +49,18 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
     extern __shared__ __align__(1024) unsigned char seg_smem_raw[];
     const uint32_t raw = smem_u32(seg_smem_raw);
     unsigned char *smem = seg_smem_raw + (((raw + 1023u) & ~1023u) - raw);   // swizzled tiles need 1024-byte alignment
-    const int nw = p.nw, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = p.nw, n_st = p.stages, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, d0 = blockIdx.x * 32 * nw;
     const bool logs = blockIdx.z != 0;
     const CUtensorMap *tm = logs ? &tm_l : &tm_m;
     float *out = logs ? p.g_logs_p : p.g_m_p;
     const uint32_t stage_bytes = (uint32_t)nw * 32u * 128u;
     unsigned char *stages = smem;
-    float *tr_all = reinterpret_cast<float *>(smem + kSegStages * stage_bytes);          // [nw][64][33]
+    float *tr_all = reinterpret_cast<float *>(smem + n_st * stage_bytes);          // [nw][64][33]
     int *nz_col = reinterpret_cast<int *>(tr_all + nw * kSegRing * 33);                   // [S]
     uint32_t *heads = reinterpret_cast<uint32_t *>(nz_col + ((p.S + 3) & ~3));            // [T / 32 + 2] bit masks
-    uint64_t *full = reinterpret_cast<uint64_t *>(heads + ((p.T / 32 + 2 + 3) & ~3));
+    uint32_t *emask = heads + ((p.T / 32 + 2 + 3) & ~3);                                  // [32]: empty columns
+    uint64_t *full = reinterpret_cast<uint64_t *>(emask + 32);
     uint64_t *empty = full + kSegStages;
     int *info = reinterpret_cast<int *>(empty + kSegStages);                              // {frames, non-empty columns}
 
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
         tma_prefetch_desc(tm);
     }
     for (int i = tid; i < p.T / 32 + 2; i += blockDim.x) heads[i] = 0u;
+    for (int s = tid; s < p.S; s += blockDim.x) nz_col[s] = max(p.dur[(size_t)b * p.S + s], 0);   // one round trip
     __syncthreads();
     if (warp == 0) {
         // The non-empty columns in order (nz_col[i]), and one bit per frame: "a column ends right before this frame"
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
         int run = 0, n_nz = 0;
         for (int s0 = 0; s0 < p.S; s0 += 32) {
             const int s = s0 + lane;
-            const int d = s < p.S ? max(p.dur[(size_t)b * p.S + s], 0) : 0;
+            const int d = s < p.S ? nz_col[s] : 0;   // compacted in place below: index i <= s, this chunk is read first
             int incl = d;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
                 if (lane >= o) incl += n;
             }
             const uint32_t m = __ballot_sync(kFullMask, d > 0);
+            if (lane == 0) emask[s0 >> 5] = ~m;
             if (d > 0) {
                 nz_col[n_nz + __popc(m & ((1u << lane) - 1u))] = s;
                 const int e = run + incl;
@@ -108,8 +111,8 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
         // ---- producer: one tile = [32 nw channels][32 frames], rows past D / frames past T arrive as zeros ----
         if (lane == 0) {
             for (int k = 0; k < n_tiles; ++k) {
-                const int st = k % kSegStages;
-                if (k >= kSegStages) mbar_wait(&empty[st], (uint32_t)((k / kSegStages - 1) & 1));
+                const int st = k % n_st;
+                if (k >= n_st) mbar_wait(&empty[st], (uint32_t)((k / n_st - 1) & 1));
                 mbar_arrive_expect_tx(&full[st], stage_bytes);
                 tma_load_3d(stages + (size_t)st * stage_bytes, tm, k * kSegFrames, d0, b, &full[st]);
             }
@@ -123,8 +126,8 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
     if (ch0 >= p.D) {
         // a warp without channels (D not a multiple of 32 nw) still frees the stages
         for (int k = 0; k < n_tiles; ++k) {
-            const int st = k % kSegStages;
-            mbar_wait(&full[st], (uint32_t)((k / kSegStages) & 1));
+            const int st = k % n_st;
+            mbar_wait(&full[st], (uint32_t)((k / n_st) & 1));
             if (lane == 0) mbar_arrive(&empty[st]);
         }
         return;
@@ -153,8 +156,8 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
     const uint32_t sw = (uint32_t)(lane & 7);
     uint32_t m = heads[0];
     for (int k = 0; k < n_tiles; ++k) {
-        const int st = k % kSegStages;
-        mbar_wait(&full[st], (uint32_t)((k / kSegStages) & 1));
+        const int st = k % n_st;
+        mbar_wait(&full[st], (uint32_t)((k / n_st) & 1));
         const uint32_t base = row + (uint32_t)st * stage_bytes;
         auto lds4 = [&](int c) {
             float4 r;
@@ -199,14 +202,14 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
     // empty columns receive nothing
     for (int s0 = 0; s0 < p.S; s0 += 32) {
         const int s = s0 + lane;
-        if (s < p.S && p.dur[(size_t)b * p.S + s] <= 0)
+        if (s < p.S && ((emask[s0 >> 5] >> lane) & 1u))
             for (int c = 0; c < nch; ++c) out_w[(size_t)c * p.S + s] = 0.0f;
     }
 }
 
-static size_t segsum_smem(int nw, int S, int T)
+static size_t segsum_smem(int nw, int stages, int S, int T)
 {
-    return 1024 + (size_t)kSegStages * nw * 32 * 128 + (size_t)nw * kSegRing * 33 * 4 + (size_t)((S + 3) & ~3) * 4 + (size_t)((T / 32 + 2 + 3) & ~3) * 4 +
+    return 1024 + (size_t)stages * nw * 32 * 128 + (size_t)nw * kSegRing * 33 * 4 + (size_t)((S + 3) & ~3) * 4 + (size_t)((T / 32 + 2 + 3) & ~3) * 4 + 32 * 4 +
            2 * kSegStages * 8 + 16;
 }
 
@@ -238,17 +241,19 @@ bool segsum_try_launch(const float *g_m, const float *g_logs, const int32_t *dur
     } else {
         tm_l = tm_m;
     }
-    const size_t smem = segsum_smem(nw, S, T);
+    int stages = config().seg_stages;
+    if (stages < 2 || stages > kSegStages) stages = 3;   // more CTAs per SM beat deeper rings (measured 3 / 4 / 6 / 8)
+    const size_t smem = segsum_smem(nw, stages, S, T);
     static thread_local int configured_dev = -1;
     if (dev != configured_dev) {
         if (cudaFuncSetAttribute(mas_segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)segsum_smem(kSegMaxWarps, MAS_MAX_TEXT, MAS_MAX_MEL)) != cudaSuccess) {
+                                 (int)segsum_smem(kSegMaxWarps, kSegStages, MAS_MAX_TEXT, MAS_MAX_MEL)) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         configured_dev = dev;
     }
-    SegParams p{dur, g_m_p, g_logs_p, D, T, S, nw};
+    SegParams p{dur, g_m_p, g_logs_p, D, T, S, nw, stages};
     const dim3 grid((unsigned)((n32 + nw - 1) / nw), (unsigned)B, g_logs ? 2u : 1u);
     mas_segsum_kernel<<<grid, 32 * (nw + 1), smem, stream>>>(tm_m, tm_l, p);
     note_launch();
