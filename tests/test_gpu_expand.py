@@ -73,12 +73,14 @@ def _segsum_reference(g, dur):
 
 
 @pytest.mark.parametrize("B,D,S,T", [(3, 192, 256, 1024), (2, 80, 97, 332), (2, 33, 600, 2000), (1, 192, 1000, 1100),
-                                     (4, 130, 50, 64), (2, 192, 31, 1000), (2, 64, 77, 301)])
+                                     (4, 130, 50, 64), (2, 192, 31, 1000), (2, 64, 77, 301), (70, 192, 40, 512),
+                                     (2, 192, 3, 4000), (3, 96, 200, 260)])
 @pytest.mark.parametrize("two", [True, False])
 def test_prior_backward_kernels_agree(cuda_device, mas_env, B, D, S, T, two):
     """The channels-on-lanes kernel (tensor-map tiles, T % 4 == 0) and the column-per-thread kernel (any T) add the
-    same frames in the same ascending order: bit-identical to each other, and equal to the fp64 sum within fp32
-    rounding.  Durations include empty columns, one very long segment, and (last utterance) columns past t_y."""
+    same frames in the same ascending order: bit-identical to each other as long as a CTA walks an utterance in one
+    run (MAS_SEG_PARTS=1; with 2 or 4 runs a column that straddles a cut is the sum of its pieces), and equal to the
+    fp64 sum within fp32 rounding either way.  Durations include empty columns, one very long segment, and (last utterance) columns past t_y."""
     g = torch.Generator().manual_seed(B * D + S)
     dur = torch.zeros((B, S), dtype=torch.int32)
     for b in range(B):
@@ -103,16 +105,24 @@ def test_prior_backward_kernels_agree(cuda_device, mas_env, B, D, S, T, two):
         torch.cuda.synchronize()
         return out_m, out_l
 
+    split_m, split_l = run()          # small batches: the frames of an utterance are cut into 2 or 4 runs per CTA
+    again_m, again_l = run()
+    assert torch.equal(split_m, again_m)            # a fixed order of additions, whatever the timing
+    mas_env(MAS_SEG_PARTS=1)
     new_m, new_l = run()
     mas_env(MAS_SEGSUM=0)
     old_m, old_l = run()
-    assert torch.equal(new_m, old_m)
+    assert torch.equal(new_m, old_m)                # one run per CTA: the very same additions
     want_m = _segsum_reference(gm, dur)
-    assert (new_m.cpu().double() - want_m).abs().max().item() <= 1e-5 * max(1.0, want_m.abs().max().item())
+    tol = 1e-5 * max(1.0, want_m.abs().max().item())
+    assert (new_m.cpu().double() - want_m).abs().max().item() <= tol
+    assert (split_m.cpu().double() - want_m).abs().max().item() <= tol
     if two:
-        assert torch.equal(new_l, old_l)
+        assert torch.equal(new_l, old_l) and torch.equal(split_l, again_l)
         want_l = _segsum_reference(gl, dur)
-        assert (new_l.cpu().double() - want_l).abs().max().item() <= 1e-5 * max(1.0, want_l.abs().max().item())
+        tol = 1e-5 * max(1.0, want_l.abs().max().item())
+        assert (new_l.cpu().double() - want_l).abs().max().item() <= tol
+        assert (split_l.cpu().double() - want_l).abs().max().item() <= tol
 
 
 @pytest.mark.parametrize("B,S,T,ragged", [(5, 80, 320, True), (2, 256, 1024, False)])

@@ -41,6 +41,8 @@ static void read_config()
     c.noise_feed = env_int("MAS_NOISE_FEED", 1);
     c.segsum = env_int("MAS_SEGSUM", 1);
     c.seg_stages = env_int("MAS_SEG_STAGES", 0);
+    c.seg_parts = env_int("MAS_SEG_PARTS", 0);
+    c.seg_nw = env_int("MAS_SEG_NW", 0);
     c.stage = env_int("MAS_STAGE", 0);
     c.tc_pair = 1;
     if (kTrace) {

@@ -51,6 +51,8 @@ struct Config {
     int noise_feed;      // MAS_NOISE_FEED=0: no {DP CTA, noise feeder CTA} pairs (helper warps inside the DP CTAs instead)
     int segsum;          // MAS_SEGSUM=0: prior-expansion backward with the column-per-thread kernel (mas_expand.cu)
     int seg_stages;      // MAS_SEG_STAGES=n: tiles in that kernel's ring (2..8; default 3)
+    int seg_parts;       // MAS_SEG_PARTS=n: runs of frames per CTA in that kernel (1, 2, 4; default: by batch size)
+    int seg_nw;          // MAS_SEG_NW=n: channel groups (of 32) per CTA in that kernel
     int stage;           // MAS_STAGE: 1 = prior preparation only, 2 = skip it (reuse the images in the workspace);
                          // bench.py times the prior kernel alone with it
     int tc_debug, dp_debug, tc_no_tma, tc_grid, tc_pair, trace;   // trace build only (MAS_TC_DEBUG, MAS_DP_DEBUG, ...)
