@@ -107,6 +107,8 @@ int mas_maximum_path_f32(const float *neg_cent, const int32_t *t_ys, const int32
  * evaluated as the reference does (two contractions over D plus two column
  * biases).  If stats_out != NULL it receives {sum, sum of squares} of all
  * B*T*S cells as two float64 (device), for the noise std of models.py:1243.
+ * S % 4 != 0: the workspace also holds a plane with 16-byte rows that the
+ * contraction stores into; a second kernel packs it into neg_cent_out.
  */
 size_t mas_neg_cent_workspace_bytes(int B, int D, int T, int S);
 int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p,
@@ -123,8 +125,10 @@ int mas_neg_cent_f32(const float *z_p, const float *m_p, const float *logs_p,
  *     and adds (std * noise) * noise_scale (:1242-1247).
  *   - neg_cent_out: optional [B,T,S] float32 copy of the cost actually aligned (with noise: the noised
  *     cost; without this request the noised plane is never written -- the DP adds the noise on the fly).
+ *     S % 4 != 0: computed into the padded plane of the workspace and packed by one more kernel.
  *   - path_out may be NULL (compact outputs only), as in mas_maximum_path_f32.
- *   - S <= 256 (any T, no multiple-of-4 requirement) and no neg_cent_out request: ONE kernel (after the prior
+ *   - no neg_cent_out request, S <= 1024 without noise / S <= 256 with noise (any T, no multiple-of-4
+ *     requirement): ONE kernel (after the prior
  *     preparation) runs contraction and DP -- concurrently without noise; with noise around a grid barrier (the
  *     statistics of models.py:1243 must exist before the first DP row), any batch size: B <= 74 with 16-byte rows
  *     of the draw runs {DP CTA, noise feeder CTA} pairs, larger batches noise-helper warps inside the DP CTAs.

@@ -10,7 +10,7 @@ for f in test_gpu_round2 test_gpu_configs test_gpu_align test_gpu_mas test_gpu_e
   tail -n 3 $O/${TAG}_pytest_$f.log
 done
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -n 1 $O/${TAG}_smoke.log
-timeout 120 python tools/bench_expand.py > $O/${TAG}_expand.log 2>&1; tail -n 6 $O/${TAG}_expand.log
+for c in c1 c2 c3 c4 c5; do timeout 120 python tools/bench_expand.py $c; done > $O/${TAG}_expand.log 2>&1; tail -n 6 $O/${TAG}_expand.log
 timeout 900 python tools/bench_configs.py c1 c2 c3 c4 c5 --json $O/${TAG}_configs.json > $O/${TAG}_configs.log 2>&1; tail -n 8 $O/${TAG}_configs.log
 timeout 400 python bench.py --steps 50 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; cut -c1-1200 $O/${TAG}_bench.json
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err; cut -c1-600 $O/${TAG}_bench_ref.json
