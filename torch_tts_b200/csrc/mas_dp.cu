@@ -100,6 +100,17 @@ bool dp_make_plan(DpPlan &pl, int B, int T, int S, int ld, int stages_hint, int 
                 if (stages_hint > 0) break;
             }
     }
+    if (ok && stages_hint <= 0 && R_hint <= 0 && !pl.p.bits_in_smem && pl.p.hop_in_smem && pl.p.R < 32) {
+        // Long utterances of wide text: the decision words are spilled anyway, and a chunk step costs ~700 cycles
+        // whatever its height -- at S = 600, T = 4000 that is 500 steps of 8 rows = 180 us of a 365 us DP.  Chunks
+        // twice as tall with the hop bytes spilled too win as long as the backtrack can bring the hops back into the
+        // idle tile ring in one sweep (dp_role): 365 -> 300 us.
+        DpPlan alt = pl;
+        bool alt_ok = false;
+        for (int st = 6; st >= W + 1 && !alt_ok; --st)
+            alt_ok = dp_plan_try(alt, T, S, ld, W, C, 2 * pl.p.R, st, false, false, budget, with_noise, false);
+        if (alt_ok && (size_t)(T / kCheck + 2) * alt.p.W * 32 * C <= (size_t)alt.p.stages * alt.p.stage_bytes) pl = alt;
+    }
     if (ok && stages_hint <= 0 && !pl.p.hop_in_smem) {
         // The search ended on the fully spilled layout.  If the same ring also fits next to on-chip hops, take
         // that: the backtrack's T/32 dependent hop reads cost ~0.6 us each from L2 and ~30 ns from shared memory

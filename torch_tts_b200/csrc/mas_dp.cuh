@@ -993,6 +993,19 @@ __device__ __forceinline__ void dp_role(const DpParams &p, unsigned char *smem, 
     // =================== backtrack ===================
     const int y_last = t_y - 1;
     const int J = t_y / kCheck;  // checkpoints stored: after rows 31, 63, ..., 32 J - 1
+    if (!kFed && !p.hop_in_smem) {
+        // Spilled hop bytes: level 1 below is J dependent reads, ~0.6 us each from L2 (75 us at T = 4000).  The tile
+        // ring is idle now -- every tile this utterance needed has been consumed -- so bring the J + 1 rows back in
+        // with coalesced loads first, when they fit.
+        const size_t need = (size_t)(J + 1) * S_pad;
+        if (need <= (size_t)p.stages * p.stage_bytes) {
+            unsigned char *hop_s = smem + p.off_stage;
+            const uint4 *src = reinterpret_cast<const uint4 *>(hop);   // region and row pitch are 16-byte multiples
+            for (size_t i = tid; i < (need + 15) / 16; i += kThreads) reinterpret_cast<uint4 *>(hop_s)[i] = src[i];
+            hop = hop_s;
+            bar_sync(bar, kThreads);
+        }
+    }
     if (tid == 0) {
         // level 1: one dependent load per 32 rows
         int c = t_x - 1;
