@@ -125,6 +125,32 @@ def test_prior_backward_kernels_agree(cuda_device, mas_env, B, D, S, T, two):
         assert (split_l.cpu().double() - want_l).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("parts", [0, 1, 2, 4])
+def test_prior_backward_degenerate_durations(cuda_device, mas_env, parts):
+    """All-empty utterances, a single column, durations that add up to more than T (clipped at T like the
+    column-per-thread kernel clips them), negative entries (treated as 0), one channel."""
+    mas_env(MAS_SEG_PARTS=parts)
+    L, p = tts._lib.lib(), tts._lib.ptr
+    cases = [
+        (torch.zeros((2, 5), dtype=torch.int32), 3, 8),
+        (torch.tensor([[8], [3]], dtype=torch.int32), 1, 8),
+        (torch.tensor([[100, 100, 100, 0, 7], [0, 0, 300, 1, 0]], dtype=torch.int32), 33, 256),
+        (torch.tensor([[-4, 2, 0, 0, 1022], [1, 1, 1, 1, 1]], dtype=torch.int32), 40, 1024),
+        (torch.full((3, 1024), 1, dtype=torch.int32), 96, 1024),
+    ]
+    for dur, D, T in cases:
+        B, S = dur.shape
+        g = torch.randn((B, D, T), generator=torch.Generator().manual_seed(S + T))
+        out = torch.full((B, D, S), float("nan"), device=cuda_device)
+        g_d, dur_d = g.to(cuda_device), dur.to(cuda_device)      # kept alive across the raw-pointer call
+        rc = L.mas_expand_prior_backward_f32(p(g_d), None, p(dur_d), p(out), None, B, D, T, S,
+                                             torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        want = _segsum_reference(g, dur)
+        assert (out.cpu().double() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()), (dur.shape, D, T)
+
+
 @pytest.mark.parametrize("B,S,T,ragged", [(5, 80, 320, True), (2, 256, 1024, False)])
 def test_logw(cuda_device, B, S, T, ragged):
     t_x, t_y, m_p, logs_p, x_mask, attn, idx, dur = _aligned(B, S, T, ragged, cuda_device, seed=9, D=8)
