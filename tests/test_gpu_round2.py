@@ -133,11 +133,13 @@ def test_wide_text_takes_the_one_kernel_path(cuda_device, B, S, T):
     assert (attn[sel].cpu() == attn_ref).float().mean().item() >= MIN_AGREE
 
 
-@pytest.mark.parametrize("B,S,T", [(80, 257, 300), (160, 131, 300), (100, 33, 700), (3, 1001, 1515)])
+@pytest.mark.parametrize("B,S,T", [(80, 257, 300), (160, 131, 300), (100, 33, 700), (3, 1001, 1515), (160, 131, 301),
+                                   (90, 200, 518), (150, 256, 262)])
 @pytest.mark.parametrize("with_noise", [False, True])
 def test_explicit_cost_plane_with_unaligned_rows(cuda_device, B, S, T, with_noise):
     """S % 4 != 0 and enough units that every contraction CTA takes several rounds: tts.neg_cent and
-    align(return_neg_cent=True) store 16-byte rows into the padded workspace plane and pack them afterwards.  The
+    align(return_neg_cent=True) store 16-byte rows into the padded workspace plane and pack them afterwards.
+    (T % 4 != 0 in the last cases: z_p has no tensor map then, the raw-z producer uses plain loads.)  The
     plane is the same run after run, matches the reference expression, and the path is its exact MAS optimum."""
     t_x, t_y, host, dev = _inputs(B, S, T, seed=S * T, dev=cuda_device)
     z_p, m_p, logs_p, x_mask, y_mask = dev
