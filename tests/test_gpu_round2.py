@@ -165,6 +165,25 @@ def test_explicit_cost_plane_with_unaligned_rows(cuda_device, B, S, T, with_nois
     assert torch.equal(idx, idx2) and torch.equal(dur, dur2)
 
 
+@pytest.mark.parametrize("B,S,T", [(80, 256, 384), (160, 131, 300), (76, 257, 301), (64, 256, 1024)])
+@pytest.mark.parametrize("no_tma", [1, 2, 3])
+def test_contraction_without_tensor_maps(cuda_device, mas_env, B, S, T, no_tma):
+    """The fallbacks for planes a tensor map cannot describe -- plain z loads (bit 1), per-cell output stores (bit 2) --
+    give the same bits as the tensor-map paths, run after run, with several rounds of units per CTA.  (The per-cell
+    stores keep the SM's load / store queue full; that is how round 2 found the converter warps handing a z stage back
+    before their shared-memory loads had read it: whole 32-row groups of neg_cent with a few channels of the wrong
+    K block.  The stage is now released after the values have been used.)"""
+    t_x, t_y, host, dev = _inputs(B, S, T, seed=B + S, dev=cuda_device)
+    z_p, m_p, logs_p, x_mask, y_mask = dev
+    want = tts.neg_cent(z_p, m_p, logs_p)
+    a0, w0, (idx0, dur0, st0) = tts.align(*dev, return_compact=True)
+    mas_env(MAS_TC_NO_TMA=no_tma)
+    for _ in range(3):
+        assert torch.equal(tts.neg_cent(z_p, m_p, logs_p), want)
+    a1, w1, (idx1, dur1, st1) = tts.align(*dev, return_compact=True)
+    assert torch.equal(idx0, idx1) and torch.equal(dur0, dur1) and torch.equal(a0, a1)
+
+
 # --------------------------------------------------------------------------
 # noise-scaled alignment in one launch
 # --------------------------------------------------------------------------

@@ -45,10 +45,10 @@ static void read_config()
     c.seg_nw = env_int("MAS_SEG_NW", 0);
     c.stage = env_int("MAS_STAGE", 0);
     c.tc_pair = 1;
+    c.tc_no_tma = env_int("MAS_TC_NO_TMA", 0);   // host-side choice of the no-tensor-map fallbacks (tests force them)
     if (kTrace) {
         c.tc_debug = env_int("MAS_TC_DEBUG", 0);
         c.dp_debug = env_int("MAS_DP_DEBUG", 0);
-        c.tc_no_tma = env_int("MAS_TC_NO_TMA", 0);
         c.tc_grid = env_int("MAS_TC_GRID", 0);
         c.tc_pair = env_int("MAS_TC_PAIR", 1);
         c.trace = env_int("MAS_TRACE", 0);

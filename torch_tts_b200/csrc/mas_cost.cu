@@ -70,9 +70,10 @@ int cost_launch(const float *z_p, const float *m_p, const float *logs_p, float *
                 const int32_t *t_ys, void *workspace, size_t workspace_bytes, int B, int D, int T, int S,
                 cudaStream_t stream, int ld)
 {
-    // rows of the output plane are `ld` floats apart and must be 16-byte multiples (tensor-map stores)
+    // rows of the output plane are `ld` floats apart; 16-byte multiples go out through the tensor-map engine, anything
+    // else through the (much slower) per-cell stores of the fallback epilogue
     if (ld <= 0) ld = S;
-    if (ld % 4 != 0 || ld < S) return MAS_ERR_ALIGNMENT;
+    if (ld < S) return MAS_ERR_ALIGNMENT;
     if (!cost_tc_supported(B, D, T, S)) return MAS_ERR_UNSUPPORTED_SHAPE;
     if (workspace_bytes < cost_workspace_bytes(B, D, T, S) || !workspace) return MAS_ERR_WORKSPACE;
     return cost_tc_launch(z_p, m_p, logs_p, neg_cent_out, stats_out, t_ys, workspace, workspace_bytes, B, D, T, S, stream,

@@ -158,7 +158,9 @@ int cost_tc_prepare(TcPlan &plan, const float *z_p, const float *m_p, const floa
     p.ld = ld;
     p.trace = trace_buffer();
     p.debug = config().tc_debug;
-    const int no_tma = config().tc_no_tma;  // trace build, A-B experiments: bit 1 plain z loads, bit 2 plain output stores
+    // MAS_TC_NO_TMA: bit 1 plain z loads, bit 2 plain output stores -- the fallbacks for pointers / pitches a tensor map
+    // cannot describe (or a driver without cuTensorMapEncodeTiled), forced by tests/test_gpu_round2.py
+    const int no_tma = config().tc_no_tma;
     // tensor maps: z_p as [B][D][T] with a [1][16][128] box, neg_cent as [B][T][ld] with a swizzled [1][32][32] box
     p.z_tma = !(no_tma & 1) && make_tmap_f32_3d(&plan.tm_z, z_p, (uint64_t)T, (uint64_t)D, (uint64_t)B, (uint64_t)T * 4,
                                                 (uint64_t)D * T * 4, kBM, kDPerKb, 1, false);
@@ -175,11 +177,6 @@ int cost_tc_launch(const float *z_p, const float *m_p, const float *logs_p, floa
     int rc = cost_tc_prepare(plan, z_p, m_p, logs_p, neg_cent_out, stats_out, t_ys, workspace, workspace_bytes, B, D, T,
                              S, nullptr, 0, stream, ld);
     if (rc) return rc;
-    // The plain-store epilogue (no tensor map for the output) is an experiment of the trace build: with several
-    // rounds of units per CTA it returned whole 32-row groups with a K block's worth of error (run-dependent,
-    // tools/debug_nc*.py in round 2), so product launches always store through the tensor map.
-    if (!kTrace && !plan.p.out_tma)
-        return MAS_ERR_UNSUPPORTED_SHAPE;
     static thread_local int configured_dev = -1;
     int dev = 0, sms = 148;
     MAS_CUDA_TRY(cudaGetDevice(&dev));

@@ -749,9 +749,13 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                     const float *zr = reinterpret_cast<const float *>(smem + Cfg::kOffZ + zs * kZStageBytes) + row;
 #pragma unroll
                     for (int d = 0; d < kDPerKb; ++d) zc[d] = zr[d * kBM];  // zero-filled past T / D by the TMA
-                    __syncwarp();
                     if (MAS_TR(p)) c2k = clock64() + (long long)(__float_as_int(zc[0]) & 0);
-                    if (lane == 0) mbar_arrive(&zempty[zs]);
+                    // The stage is handed back further down, once the values have been USED.  Arriving on zempty right
+                    // here (16 LDS issued, none consumed) let the arrive overtake the loads: SYNCS.ARRIVE does not wait
+                    // in the shared-memory load queue, so when that queue is long (the plain-store epilogue's scattered
+                    // STGs) the producer's next TMA fill of the stage -- K block kb + 6 -- landed before the last LDS had
+                    // read it, and a warp's 32 rows got a few channels of the wrong K block (found in round 2 as
+                    // run-dependent 32-row groups of neg_cent with rank-2..12 errors, tools/debug_plain.py).
                 } else {
                     const int d0 = kb * kDPerKb;
 #pragma unroll
@@ -785,6 +789,8 @@ __device__ __forceinline__ void cost_tc_role(const TcParams &p, const CUtensorMa
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) {
+                    // every lane's stores above took the z values as operands, so the loads are done: free the z stage
+                    if (p.z_tma && !MAS_DBG(p, 32)) mbar_arrive(&zempty[it % kZStages]);
                     if (kPair)
                         mbar_arrive_cluster(full0 + s * 8u);
                     else
