@@ -22,7 +22,8 @@ bool make_tmap_f32_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t 
 
 constexpr int kSegFrames = 32;     // frames per tile row: 128 bytes, one swizzle atom
 constexpr int kSegStages = 8;     // most tiles in the ring (the launch picks how many are used)
-constexpr int kSegRing = 64;      // parked column sums per warp (at most 4 close per step of 4 frames, 32 leave at a time)
+constexpr int kSegRing = 32;      // parked column sums per warp (at most 4 close per step of 4 frames, 16 leave at a time)
+constexpr int kSegOut = 16;       // columns per write-out: half a warp per column block, the halves take 16 channels each
 constexpr int kSegMaxWarps = 8;    // consumer warps per CTA (32 channels each); one more warp issues the loads
 constexpr int kSegMaxParts = 4;    // runs of frames per CTA, each with its own ring and consumer warps
 
@@ -32,8 +33,9 @@ struct SegParams {
     int D, T, S, nw, np, stages;
 };
 
-// 32 parked sums x up to 32 channels of one warp -> g_in (lane = one non-empty column, neighbouring lanes are
-// neighbouring columns unless an empty one lies between).  Out of line: it runs once per 32 columns.
+// 16 parked sums x up to 32 channels of one warp -> g_in (a lane = one non-empty column and one half of the channels;
+// neighbouring lanes are neighbouring columns unless an empty one lies between).  Out of line: it runs once per 16
+// columns.
 __device__ __noinline__ void seg_write_block(const float *tr_row, float *dst, int nch, int S, bool on)
 {
     __syncwarp();
@@ -44,7 +46,7 @@ __device__ __noinline__ void seg_write_block(const float *tr_row, float *dst, in
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
+__global__ void __launch_bounds__(32 * (kSegMaxWarps + kSegMaxParts))
     mas_segsum_kernel(const __grid_constant__ CUtensorMap tm_m, const __grid_constant__ CUtensorMap tm_l, SegParams p)
 {
     extern __shared__ __align__(1024) unsigned char seg_smem_raw[];
@@ -116,13 +118,14 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
     const int tpp = (n_tiles + np - 1) / np;
     const int p_last = n_tiles > 0 ? (n_tiles - 1) / tpp : 0;
 
-    if (warp == n_cons) {
-        // ---- producer: lane r feeds the ring of part r.  One tile = [32 nw channels][32 frames]; rows past D and
-        // frames past T arrive as zeros ----
-        if (lane < np) {
-            const int k0 = lane * tpp, n = max(0, min(tpp, n_tiles - k0));
-            uint64_t *fl = full + lane * kSegStages, *em = empty + lane * kSegStages;
-            unsigned char *ring = rings + (size_t)lane * n_st * stage_bytes;
+    if (warp >= n_cons) {
+        // ---- producers: warp n_cons + r feeds the ring of part r.  One tile = [32 nw channels][32 frames]; rows past D
+        // and frames past T arrive as zeros ----
+        const int r = warp - n_cons;
+        if (lane == 0) {
+            const int k0 = r * tpp, n = max(0, min(tpp, n_tiles - k0));
+            uint64_t *fl = full + r * kSegStages, *em = empty + r * kSegStages;
+            unsigned char *ring = rings + (size_t)r * n_st * stage_bytes;
             for (int j = 0; j < n; ++j) {
                 const int st = j % n_st;
                 if (j >= n_st) mbar_wait(&em[st], (uint32_t)((j / n_st - 1) & 1));
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
     const int part = warp / nw, cg = warp - part * nw;
     const int k0 = part * tpp, n_mine = max(0, min(tpp, n_tiles - k0));
     uint64_t *fl = full + part * kSegStages, *em = empty + part * kSegStages;
-    float *tr = tr_all + warp * kSegRing * 33;   // ring of parked sums: [non-empty column index & 63][channel]
+    float *tr = tr_all + warp * kSegRing * 33;   // ring of parked sums: [non-empty column index & 31][channel]
     const int ch0 = d0 + cg * 32;
     const bool have_ch = ch0 < p.D;              // D not a multiple of 32 nw: a warp without channels only frees the stages
     const int nch = min(32, p.D - ch0);
@@ -151,12 +154,14 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
     // an earlier part and is finished there
     float *slot = part == 0 ? tr + (i_cur & (kSegRing - 1)) * 33 + lane : fp_all + warp * 32 + lane;
     float acc = 0.0f;
-    auto write_blocks = [&](int upto) {   // 32 parked sums at a time; the last call takes what is left
+    auto write_blocks = [&](int upto) {   // 16 parked sums at a time; the last call takes what is left
+        const int col = lane & (kSegOut - 1), c0 = (lane >> 4) * 16;
         while (i_out < upto) {
-            const int i = i_out + lane;
-            const bool on = i < upto;
-            seg_write_block(tr + (i & (kSegRing - 1)) * 33, out_w + (on ? nz_col[i] : 0), nch, p.S, on);
-            i_out += 32;
+            const int i = i_out + col;
+            const bool on = i < upto && c0 < nch;
+            seg_write_block(tr + (i & (kSegRing - 1)) * 33 + c0, out_w + (size_t)c0 * p.S + (on ? nz_col[i] : 0),
+                            min(16, nch - c0), p.S, on);
+            i_out += kSegOut;
         }
     };
 #define MAS_SEG_CLOSE()                                       \
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
                     MAS_SEG_STEP(cur.y, 2u)
                     MAS_SEG_STEP(cur.z, 4u)
                     MAS_SEG_STEP(cur.w, 8u)
-                    if (i_cur - i_out >= 32) write_blocks(i_out + ((i_cur - i_out) & ~31));
+                    if (i_cur - i_out >= kSegOut) write_blocks(i_out + ((i_cur - i_out) & ~(kSegOut - 1)));
                 }
                 cur = nxt;
             }
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + 1))
             // the column that ends at t_end, and (durations adding up to more than T) the ones that never started
             while (i_cur < n_nz) {
                 MAS_SEG_CLOSE()
-                if (i_cur - i_out >= 32) write_blocks(i_out + ((i_cur - i_out) & ~31));
+                if (i_cur - i_out >= kSegOut) write_blocks(i_out + ((i_cur - i_out) & ~(kSegOut - 1)));
             }
         }
         tail_all[warp * 32 + lane] = acc;
@@ -324,7 +329,7 @@ bool segsum_try_launch(const float *g_m, const float *g_logs, const int32_t *dur
     if (smem > segsum_smem(4, 2, kSegStages / 2, MAS_MAX_TEXT, MAS_MAX_MEL)) return false;
     SegParams p{dur, g_m_p, g_logs_p, D, T, S, nw, np, stages};
     const dim3 grid((unsigned)((n32 + nw - 1) / nw), (unsigned)B, (unsigned)ntens);
-    mas_segsum_kernel<<<grid, 32 * (nw * np + 1), smem, stream>>>(tm_m, tm_l, p);
+    mas_segsum_kernel<<<grid, 32 * (nw * np + np), smem, stream>>>(tm_m, tm_l, p);
     note_launch();
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) *rc = note_cuda_error(e, "mas_segsum_kernel");
