@@ -535,8 +535,6 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
 #pragma unroll
                     for (int k = 0; k < KQ; ++k)
                         if (gl + k * HT < n4) cv[k] = t4[k * HT], nv[k] = nz4[k * HT];
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&nfree[h]);   // this warp has read the half: the next chunk's may come
 #pragma unroll
                     for (int k = 0; k < KQ; ++k)
                         if (gl + k * HT < n4) {
@@ -546,6 +544,10 @@ __device__ __noinline__ void dp_noise_helper(const DpParams &p, unsigned char *s
                             cv[k].w = __fadd_rn(cv[k].w, __fmul_rn(__fmul_rn(sd, nv[k].w), scale));
                             t4[k * HT] = cv[k];
                         }
+                    // The half goes back only now: the stores above took every loaded value as an operand, so the loads
+                    // are done.  (An arrive issued right after the loads can overtake them, see cost_tc_role's converters.)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&nfree[h]);
                 } else {
                     // rows that are not a multiple of 16 bytes (real collated batches: data_utils.py:151-214): the
                     // draw is packed with stride S, the private cost plane has stride ld; one element at a time

@@ -156,8 +156,17 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
 #pragma unroll
                     for (int k = 0; k < KQ; ++k)
                         if (gl + k * HT < n4) cv[k] = c4[k * HT], nv[k] = z4[k * HT];
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&fempty[s]);            // this warp has read the stage
+                    // (the stage is NOT handed back here: an arrive issued right after the loads does not queue behind
+                    // them in the shared-memory pipe and the producer's refill can land first; see cost_tc_role's
+                    // converters.  It goes back after the stores below.)
+#pragma unroll
+                    for (int k = 0; k < KQ; ++k)
+                        if (gl + k * HT < n4) {
+                            cv[k].x = __fadd_rn(cv[k].x, __fmul_rn(__fmul_rn(sd, nv[k].x), scale));
+                            cv[k].y = __fadd_rn(cv[k].y, __fmul_rn(__fmul_rn(sd, nv[k].y), scale));
+                            cv[k].z = __fadd_rn(cv[k].z, __fmul_rn(__fmul_rn(sd, nv[k].z), scale));
+                            cv[k].w = __fadd_rn(cv[k].w, __fmul_rn(__fmul_rn(sd, nv[k].w), scale));
+                        }
                     const long long f2 = MAS_TR(fp.tc) ? clock64() : 0;
                     if (lane == 0) mbar_wait_acq_cluster(&credit[st], (ud & 1u) ^ 1u);   // the partner has consumed the stage's previous tile
                     __syncwarp();
@@ -166,15 +175,15 @@ __device__ __forceinline__ void noise_feeder_role(const FusedParams &fp, unsigne
 #pragma unroll
                     for (int k = 0; k < KQ; ++k)
                         if (gl + k * HT < n4) {
-                            cv[k].x = __fadd_rn(cv[k].x, __fmul_rn(__fmul_rn(sd, nv[k].x), scale));
-                            cv[k].y = __fadd_rn(cv[k].y, __fmul_rn(__fmul_rn(sd, nv[k].y), scale));
-                            cv[k].z = __fadd_rn(cv[k].z, __fmul_rn(__fmul_rn(sd, nv[k].z), scale));
-                            cv[k].w = __fadd_rn(cv[k].w, __fmul_rn(__fmul_rn(sd, nv[k].w), scale));
                             // asynchronous store: counted on the partner's full barrier of the stage, which its
                             // producer lane has armed with the tile's byte count (no fence, no arrive here: a
                             // release-arrive per warp and tile cost the feeder 1.9 us per chunk)
                             dsm_st_async_v4(dst + (uint32_t)(k * HT) * 16u, cv[k], r_full0 + st * 8u);
                         }
+                    // The stage goes back to the producer only now: the stores above (memory operations, which the
+                    // release-arrive cannot pass) took every loaded value as an operand, so the loads are done.
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fempty[s]);
                     if (MAS_TR(fp.tc)) {
                         const long long f4 = clock64();
                         facc[0] += f1 - f0, facc[1] += f2 - f1, facc[2] += f3 - f2, facc[3] += f4 - f3;

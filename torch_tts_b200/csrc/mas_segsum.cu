@@ -210,7 +210,12 @@ __global__ void __launch_bounds__(32 * (kSegMaxWarps + kSegMaxParts))
                 cur = nxt;
             }
             m = m_next;
-            __syncwarp();   // every lane has used its copy of the tile
+            // The tile goes back once its values have been consumed.  The store makes that explicit for the hardware
+            // AND the compiler: it takes the running sum (hence every load of this tile) as its operand, and a memory
+            // operation cannot move below the release-arrive, whereas the additions alone could be scheduled after it
+            // (an arrive that overtakes pending shared-memory loads lets the refill land first: cost_tc_role).
+            tail_all[warp * 32 + lane] = acc;
+            __syncwarp();
             if (lane == 0) mbar_arrive(&em[st]);
         }
         if (part == p_last) {
