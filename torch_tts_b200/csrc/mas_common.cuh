@@ -55,7 +55,9 @@ struct Config {
     int seg_nw;          // MAS_SEG_NW=n: channel groups (of 32) per CTA in that kernel
     int stage;           // MAS_STAGE: 1 = prior preparation only, 2 = skip it (reuse the images in the workspace);
                          // bench.py times the prior kernel alone with it
-    int tc_debug, dp_debug, tc_no_tma, tc_grid, tc_pair, trace;   // trace build only (MAS_TC_DEBUG, MAS_DP_DEBUG, ...)
+    int tc_no_tma;       // MAS_TC_NO_TMA: bit 1 plain z loads, bit 2 per-cell output stores -- the contraction's fallbacks for
+                         // planes no tensor map describes; a host-side choice, forced by the parity tests
+    int tc_debug, dp_debug, tc_grid, tc_pair, trace;   // trace build only (MAS_TC_DEBUG, MAS_DP_DEBUG, ...)
 };
 const Config &config();
 
