@@ -165,7 +165,10 @@ int mas_expand_path(const int32_t *idx, void *path_out, int path_dtype,
  * mas_expand_prior_backward_f32 -- the gradient of that expansion with respect to m_p / logs_p
  *   (what autograd derives from the two matmuls): g_m_p[b,d,s] = sum of g_m[b,d,t] over the frames
  *   aligned to s, i.e. t in [start_s, start_s + dur[b,s]) with start = exclusive prefix sum of dur[b,:].
- *   Fixed summation order, no atomics.  g_logs / g_logs_p may both be NULL.
+ *   Fixed summation order (ascending t; small batches sum a column that straddles a cut of the frame range from
+ *   its pieces, the same way on every run), no atomics.  g_logs / g_logs_p may both be NULL.  Negative durations
+ *   count as 0, frames past T are not read.  T % 4 == 0 with 16-byte aligned gradients takes the tensor-map kernel
+ *   (csrc/mas_segsum.cu), anything else the column-per-thread kernel.
  *
  * mas_logw_f32 -- replaces models.py:1256 + 1261:  w = attn.sum(2);  logw_ = torch.log(w + 1e-6) * x_mask
  *   from the int32 durations [B,S] and the text lengths [B]; output [B,S] fp32.
