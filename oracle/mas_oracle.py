@@ -152,6 +152,27 @@ def expand_prior_torch(attn, m_p, logs_p):
     return m, l
 
 
+def expand_prior_backward_np(g, dur):
+    """Backward of expand_prior_torch with respect to m_p (or logs_p) from the durations: what autograd derives from
+    models.py:1270-1271 is `attn^T g`, and with a monotonic one-hot path the frames of column s are the contiguous
+    range [start_s, start_s + dur_s), start = exclusive prefix sum of the durations.  g [B,D,T] -> fp64 [B,D,S];
+    negative durations count as 0, frames past T do not exist (the contract of mas_expand_prior_backward_f32)."""
+    g = np.asarray(g, dtype=np.float64)
+    dur = np.asarray(dur)
+    B, D, T = g.shape
+    S = dur.shape[1]
+    out = np.zeros((B, D, S), dtype=np.float64)
+    for b in range(B):
+        start = 0
+        for s in range(S):
+            n = max(int(dur[b, s]), 0)
+            lo, hi = min(start, T), min(start + n, T)
+            if hi > lo:
+                out[b, :, s] = g[b, :, lo:hi].sum(1)
+            start += n
+    return out
+
+
 def logw_torch(attn, x_mask):
     """models.py:1256 + 1261: w = attn.sum(2); logw_ = log(w + 1e-6) * x_mask."""
     import torch

@@ -56,20 +56,8 @@ def test_expand_prior_backward_matches_autograd_of_the_matmuls(cuda_device, B, S
 
 
 def _segsum_reference(g, dur):
-    """fp64 segmented sum on the host: g [B,D,T], dur [B,S] -> [B,D,S]"""
-    B, D, T = g.shape
-    S = dur.shape[1]
-    out = torch.zeros((B, D, S), dtype=torch.float64)
-    g64 = g.double()
-    for b in range(B):
-        start = 0
-        for s in range(S):
-            n = max(int(dur[b, s]), 0)
-            lo, hi = min(start, T), min(start + n, T)
-            if hi > lo:
-                out[b, :, s] = g64[b, :, lo:hi].sum(1)
-            start += n
-    return out
+    """fp64 segmented sum on the host (the oracle's restatement, pinned against autograd in tests/test_oracle.py)"""
+    return torch.from_numpy(mas_oracle.expand_prior_backward_np(g.numpy(), dur.numpy()))
 
 
 @pytest.mark.parametrize("B,D,S,T", [(3, 192, 256, 1024), (2, 80, 97, 332), (2, 33, 600, 2000), (1, 192, 1000, 1100),

@@ -200,3 +200,20 @@ def test_consumers_golden():
     m_p = z["m_p"]
     gathered = np.where(idx[:, None, :] >= 0, np.take_along_axis(m_p, np.maximum(idx, 0)[:, None, :].repeat(m_p.shape[1], 1), 2), 0)
     assert np.array_equal(gathered.astype(np.float32), z["m_expanded"])
+
+
+def test_expand_prior_backward_restated_from_durations():
+    """The durations form of the prior-expansion backward (oracle.expand_prior_backward_np, the checker of the CUDA
+    segmented sum) against autograd of the reference's own two matmuls (models.py:1270-1271) on the golden path."""
+    z = _npz("consumers.npz")
+    attn = torch.from_numpy(z["attn"])
+    m_p = torch.from_numpy(z["m_p"]).double().requires_grad_(True)
+    logs_p = torch.from_numpy(z["logs_p"]).double().requires_grad_(True)
+    m_e, l_e = mas_oracle.expand_prior_torch(attn.double(), m_p, logs_p)
+    g = torch.Generator().manual_seed(4)
+    gm, gl = torch.randn(m_e.shape, generator=g, dtype=torch.float64), torch.randn(l_e.shape, generator=g, dtype=torch.float64)
+    (m_e * gm).sum().add((l_e * gl).sum()).backward()
+    dur = attn.squeeze(1).sum(1).round().int().numpy()                 # w = attn.sum(2) of models.py:1256, [B,S]
+    assert np.allclose(mas_oracle.expand_prior_backward_np(gm.numpy(), dur), m_p.grad.numpy(), rtol=0, atol=1e-12)
+    assert np.allclose(mas_oracle.expand_prior_backward_np(gl.numpy(), dur), logs_p.grad.numpy(), rtol=0, atol=1e-12)
+
